@@ -1,0 +1,163 @@
+/* mlcg.h -- C ABI of libmlcg_b200.so: the sm_100a implementation of ml_conformer_generator's data-parallel hot path
+ * (batched EDM reverse diffusion with the EGNN denoiser, then the AdjMatSeer bond-order GCN).
+ *
+ * The reference (Membrizard/ml_conformer_generator) is pure Python/torch and has no FFI layer; its seams for this
+ * path are Python call sites.  Each entry point below names the reference call it replaces (file:line relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  Unless a parameter says "host", pointers are DEVICE pointers
+ *    owned by the caller; the library never frees caller memory.
+ *  - every call enqueues its work on `stream` (a cudaStream_t passed as void*) and returns without synchronising,
+ *    except mlcg_generate / mlcg_load_* / mlcg_set_batch which are synchronous.
+ *  - return value: 0 = ok, < 0 = argument / state error (see mlcg_last_error), > 0 = cudaError_t.
+ *  - one handle per (device, stream); a handle is thread-compatible, not thread-safe.
+ *  - layouts are the reference's: z / eps / noise are (B, N, 11) float32 row-major with N = the call's max_n_nodes
+ *    (3 coordinates, then 8 atom-class channels); atoms of a sample occupy the first n_nodes[b] slots ("prefix"
+ *    node mask, reference utils/mol_utils.py:241-243); padded slots are written as exact zeros.
+ *  - there is no CPU fallback: every function fails loudly (MLCG_E_NO_DEVICE) if no sm_100 device is present.
+ */
+#ifndef MLCG_H_
+#define MLCG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlcg_handle mlcg_handle;
+
+/* precision of the EGNN edge / node GEMMs */
+enum {
+  MLCG_PREC_FP32 = 0, /* exact fp32 SIMT kernels (on-GPU reference mode; edge tensors staged through HBM) */
+  MLCG_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate -- parity mode (eps within 1e-3 relative) */
+  MLCG_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream -- fast mode */
+};
+
+enum {
+  MLCG_OK = 0,
+  MLCG_E_ARG = -1,       /* bad argument / shape */
+  MLCG_E_STATE = -2,     /* weights or batch not set */
+  MLCG_E_NO_DEVICE = -3, /* no sm_100 CUDA device: this library has no fallback */
+  MLCG_E_WEIGHT = -4     /* missing / mis-shaped state_dict entry */
+};
+
+/* One state_dict entry: reference key name, fp32 DEVICE pointer, shape (rows = size(0), cols = numel/size(0)). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int rows;
+  int cols;
+} mlcg_weight_desc;
+
+/* Noise source for one draw of sample_combined_position_feature_noise (equivariant_diffusion.py:341-363).
+ * raw != NULL : (B, N, 11) raw N(0,1) draws injected by the caller (parity mode; x-part first, then h-part);
+ * raw == NULL : device Philox4x32-10 keyed by (seed, sample_offset + b, atom, draw) -- results do not depend on how a
+ *               batch is sharded across GPUs. */
+typedef struct {
+  const float* raw;
+  uint64_t seed;
+  uint64_t draw;
+  int64_t sample_offset;
+} mlcg_noise;
+
+/* Scalars of one reverse step, computed on the host exactly as the reference does in float32 torch
+ * (equivariant_diffusion.py:224-247, 305-326): z_s = z_t/alpha_ts - c_eps*eps + c_sigma*noise. */
+typedef struct {
+  float t;        /* (s+1)/T, fed to the denoiser */
+  float alpha_ts; /* alpha_{t|s} */
+  float c_eps;    /* sigma2_{t|s} / alpha_{t|s} / sigma_t */
+  float c_sigma;  /* sigma_{t|s} * sigma_s / sigma_t */
+  float alpha_s;  /* forward-diffusion of the fixed fragment (inpaint / merge) */
+  float sigma_s;
+  float blend;    /* (1 - s/T)^blend_power */
+} mlcg_step_scalars;
+
+const char* mlcg_version(void);
+
+/* Replaces: module construction + .to(device) in MLConformerGenerator.__init__ (conformer_generator.py:67-123). */
+int mlcg_create(mlcg_handle** out, int device, int precision);
+void mlcg_destroy(mlcg_handle* h);
+const char* mlcg_last_error(mlcg_handle* h);
+
+/* Replaces: generative_model.load_state_dict(...) (conformer_generator.py:90-95).  Keys: "dynamics.egnn.*" exactly as
+ * in EquivariantDiffusion.state_dict(); "gamma.gamma" is ignored (the schedule is rebuilt on the host for the
+ * requested step count, conformer_generator.py:104-113).  Repacks / pads / casts once; synchronous. */
+int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n);
+/* Replaces: adj_mat_seer.load_state_dict(...) (conformer_generator.py:97-102). */
+int mlcg_load_seer(mlcg_handle* h, const mlcg_weight_desc* w, int n);
+
+/* Replaces: prepare_masks (utils/mol_utils.py:226-252) + EGNNDynamics.get_adj_matrix (egnn.py:515-541): fixes the
+ * batch geometry (n_nodes_host[b] atoms in sample b, padded to N slots), builds the edge-tile table and sizes the
+ * workspaces.  n_nodes_host is a HOST array.  1 <= n_nodes[b] <= N <= 39. */
+int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N);
+
+/* Replaces: EGNNDynamics.forward (egnn.py:472-513), i.e. `dynamics(t, xh, node_mask, edge_mask, context)`.
+ * t: (B) per-sample time; z: (B,N,11); ctx: (B,3) normalised context per sample; eps out: (B,N,11). */
+int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z, const float* ctx, float* eps, void* stream);
+
+/* Replaces: sample_combined_position_feature_noise as used for the initial latent (equivariant_diffusion.py:384). */
+int mlcg_noise_init(mlcg_handle* h, float* z, const mlcg_noise* noise, void* stream);
+/* Replaces: the arithmetic of sample_p_zs_given_zt after the network call (equivariant_diffusion.py:320-338). */
+int mlcg_step(mlcg_handle* h, float* z, const float* eps, const mlcg_step_scalars* sc, const mlcg_noise* noise,
+              void* stream);
+/* Replaces: fragment re-injection of inpaint / merge_fragments (equivariant_diffusion.py:473-493, 79-105).
+ * z_known: (B,N,11); fixed_mask: (B,N) float 0/1. */
+int mlcg_reinject(mlcg_handle* h, float* z, const float* z_known, const float* fixed_mask, const mlcg_step_scalars* sc,
+                  const mlcg_noise* noise, void* stream);
+/* Replaces: z = alpha*z_known + sigma*eps at diffusion_level (equivariant_diffusion.py:549-559). */
+int mlcg_forward_diffuse(mlcg_handle* h, float* z, const float* z_known, float alpha, float sigma,
+                         const mlcg_noise* noise, void* stream);
+/* Replaces: sample_p_xh_given_z0 after the network call (equivariant_diffusion.py:269-285).
+ * x out: (B,N,3); atom_class out: (B,N) int32 in 0..6, -1 for padded slots. */
+int mlcg_decode(mlcg_handle* h, const float* z0, const float* eps0, float sigma_0, float alpha_0, float sigma_x,
+                const mlcg_noise* noise, float* x, int32_t* atom_class, void* stream);
+
+/* Whole reverse loop on the device.  mode 0 = EquivariantDiffusion.forward (equivariant_diffusion.py:365-421),
+ * 1 = .inpaint (:423-513), 2 = .merge_fragments (:515-607).  steps: HOST array of T entries, steps[s] for integer
+ * step s (s = T-1 .. 0 are executed; merge skips s > diffusion_level).  ctx: (B,3).  noise_tape: NULL (device
+ * Philox, seed) or (n_draws, B, N, 11) raw draws consumed in the reference's order.  z_work: (B,N,11) scratch that
+ * holds z_0 on return.  trace_z / trace_eps: optional (n_forwards, B, N, 11) outputs recording every denoiser
+ * input / output (parity tests), or NULL. */
+int mlcg_sample(mlcg_handle* h, int mode, int T, const mlcg_step_scalars* steps, int resample_steps,
+                int diffusion_level, float merge_alpha, float merge_sigma, float sigma_0, float alpha_0, float sigma_x,
+                const float* ctx, const float* z_known, const float* fixed_mask, const float* noise_tape,
+                uint64_t seed, int64_t sample_offset, float* z_work, float* x_out, int32_t* atom_class_out,
+                float* trace_z, float* trace_eps, void* stream);
+
+/* Replaces (tensor part, declared connectivity rule -- see DESIGN.md): prepare_adj_mat_seer_input
+ * (utils/mol_utils.py:159-191).  x: (B,N,3), atom_class: (B,N) -> elements (B,42) int32, dist (B,42,42), adj (B,42,42). */
+int mlcg_seer_inputs(mlcg_handle* h, const float* x, const int32_t* atom_class, int32_t* elements, float* dist,
+                     float* adj, void* stream);
+/* Replaces: AdjMatSeer.forward (adj_mat_seer.py:104-165) + the argmax of redefine_bonds (utils/mol_utils.py:210-211).
+ * elements (B,42) int32; dist, adj (B,42,42) incl. +I; logits out (B,42,42,5) or NULL; bonds out (B,42,42) int8 or
+ * NULL (lower triangle, zero diagonal).  B here is independent of mlcg_set_batch. */
+int mlcg_seer_forward(mlcg_handle* h, const int32_t* elements, const float* dist, const float* adj, float* logits,
+                      int8_t* bonds, int B, void* stream);
+
+/* End-to-end call with HOST buffers (what MLConformerGenerator.generate_tensors uses): uploads n_nodes / context,
+ * runs mlcg_set_batch + mlcg_sample(mode 0) + mlcg_seer_inputs + mlcg_seer_forward, downloads results.
+ * n_nodes_host (B), ctx_host (B,3) -> x_host (B,N,3), atom_class_host (B,N) int32, bonds_host (B,42,42) int8. */
+int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, const float* ctx_host, int T,
+                  const mlcg_step_scalars* steps, int resample_steps, float sigma_0, float alpha_0, float sigma_x,
+                  uint64_t seed, int64_t sample_offset, float* x_host, int32_t* atom_class_host, int8_t* bonds_host,
+                  void* stream);
+
+/* Introspection for benches / tests. */
+int mlcg_num_edge_tiles(mlcg_handle* h);
+int64_t mlcg_num_edges(mlcg_handle* h);          /* sum_b n_b (n_b - 1) */
+int64_t mlcg_kernel_launches(mlcg_handle* h);    /* kernels launched by this handle since creation */
+/* Times the dominant kernel (the fused edge kernel) with CUDA events on `stream`: runs one sub-layer launch `iters`
+ * times on the current batch state and returns the mean milliseconds per launch (< 0 on error). */
+float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, void* stream);
+
+/* Test hook: C[M x N] = A[M x K] . W[N x K]^T + bias through the tcgen05 GEMM kernel (row-major fp32 in / out,
+ * converted to operand format internally).  mode = MLCG_PREC_TF32 or MLCG_PREC_BF16; bn = 448 or 256. */
+int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,
+                   int M, int N, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLCG_H_ */

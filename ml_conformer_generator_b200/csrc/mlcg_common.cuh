@@ -1,0 +1,240 @@
+// Shared device helpers for the sm_100a kernels: PTX wrappers (mbarrier, bulk async copy, tcgen05 / TMEM),
+// operand-tile geometry, activation functions.  Everything here is hand-written for sm_100a; there is no
+// fallback path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mlcg {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Geometry of the hot path (reference conformer_generator.py:67-88)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int HID = 420;        // hidden_nf
+constexpr int HP = 448;         // HID padded to 7 x 64 (clean 128-byte swizzle atoms)
+constexpr int BIAS_COL = 420;   // spare K column carrying the folded bias of the 2nd edge layer
+constexpr int IN_NF = 12;       // 8 classes + time + 3 context
+constexpr int ZC = 11;          // latent channels: 3 coords + 8 classes
+constexpr int TILE_M = 128;     // rows per tensor-core tile (= TMEM lanes)
+constexpr int CHUNK_BYTES = 128;                      // K bytes per operand chunk row (one SWIZZLE_128B atom row)
+constexpr int A_CHUNK_BYTES = TILE_M * CHUNK_BYTES;   // 16 KB: one [128 x 128 B] A-operand chunk
+constexpr int SEER_D = 42;
+constexpr int SEER_H = 2048;
+constexpr int SEER_E = 64;
+constexpr int SEER_NB = 5;
+
+enum Precision { PREC_FP32_SIMT = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
+
+// elements per 128-byte operand chunk row
+__host__ __device__ constexpr int epc(int mode) { return mode == PREC_BF16 ? 64 : 32; }
+// elements per 16-byte piece
+__host__ __device__ constexpr int epp(int mode) { return mode == PREC_BF16 ? 8 : 4; }
+
+// byte offset of (row r, 16-byte piece p) inside a SWIZZLE_128B K-major chunk whose base is 1024-byte aligned:
+// Swizzle<3,4,3>: address bits [4,7) ^= bits [7,10).
+__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t p) {
+  return r * 128u + ((p ^ (r & 7u)) << 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// activations
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kFast>
+__device__ __forceinline__ float silu(float x) {
+  if constexpr (kFast) {
+    // x*sigmoid(x) = h + h*tanh(h), h = x/2 : one MUFU op
+    float h = 0.5f * x, t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  } else {
+    return __fdividef(x, 1.0f + __expf(-x));
+  }
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// full-precision SiLU for the fp32 SIMT path
+__device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ uint32_t f32_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory addresses, mbarriers, proxies
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Wait for the phase with the given parity to complete.  A protocol bug must not hang the GPU: after ~4 s of
+// spinning the kernel traps, which surfaces as a CUDA error on the host.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {
+        printf("mlcg: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------------------------------
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // the same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor for a K-major, SWIZZLE_128B operand whose rows are 128 bytes (one swizzle atom
+// wide in K): 8-row groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major; version = 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                        // leading byte offset (unused)
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type: SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor: D = fp32, A/B K-major, dense.  fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt, int m, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+template <int kMode>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kMode == PREC_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand-format stores: activations that feed a tensor-core GEMM live in HBM as [m_tile][k_chunk][128 x 128 B]
+// blocks that are byte-for-byte the SWIZZLE_128B shared-memory image, so a stage is one contiguous bulk copy.
+// ---------------------------------------------------------------------------------------------------------------
+template <int kMode>
+__device__ __forceinline__ size_t op_tile_bytes(int n_chunks) { return (size_t)n_chunks * A_CHUNK_BYTES; }
+
+// store `kCount` (multiple of epp) consecutive K elements of operand row `grow`, starting at K index `k0`
+// (k0 % epp == 0), into an operand-format array with `n_chunks` chunks per tile.
+template <int kMode, int kCount>
+__device__ __forceinline__ void op_store(uint8_t* base, int n_chunks, int grow, int k0, const float* v) {
+  constexpr int EPC = epc(kMode), EPP = epp(kMode);
+  const int mt = grow >> 7, r = grow & 127;
+#pragma unroll
+  for (int e = 0; e < kCount; e += EPP) {
+    const int k = k0 + e;
+    const int kc = k / EPC, p = (k % EPC) / EPP;
+    uint8_t* dst = base + ((size_t)mt * n_chunks + kc) * A_CHUNK_BYTES + sw128_offset(r, p);
+    uint4 w;
+    if constexpr (kMode == PREC_BF16) {
+      w.x = pack_bf16x2(v[e + 0], v[e + 1]);
+      w.y = pack_bf16x2(v[e + 2], v[e + 3]);
+      w.z = pack_bf16x2(v[e + 4], v[e + 5]);
+      w.w = pack_bf16x2(v[e + 6], v[e + 7]);
+    } else {
+      w.x = f32_to_tf32(v[e + 0]);
+      w.y = f32_to_tf32(v[e + 1]);
+      w.z = f32_to_tf32(v[e + 2]);
+      w.w = f32_to_tf32(v[e + 3]);
+    }
+    *reinterpret_cast<uint4*>(dst) = w;
+  }
+}
+// single element store (used by the segment-sum readers, one column per lane)
+template <int kMode>
+__device__ __forceinline__ void op_store1(uint8_t* base, int n_chunks, int grow, int k, float v) {
+  constexpr int EPC = epc(kMode), EPP = epp(kMode);
+  const int mt = grow >> 7, r = grow & 127;
+  const int kc = k / EPC, within = k % EPC;
+  uint8_t* dst = base + ((size_t)mt * n_chunks + kc) * A_CHUNK_BYTES + sw128_offset(r, within / EPP);
+  if constexpr (kMode == PREC_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(dst)[within % EPP] = __float2bfloat16_rn(v);
+  } else {
+    reinterpret_cast<uint32_t*>(dst)[within % EPP] = f32_to_tf32(v);
+  }
+}
+
+}  // namespace mlcg
