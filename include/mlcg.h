@@ -152,6 +152,12 @@ int64_t mlcg_kernel_launches(mlcg_handle* h);    /* kernels launched by this han
  * times on the current batch state and returns the mean milliseconds per launch (< 0 on error). */
 float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, void* stream);
 
+/* Diagnostics: mean cycles per 128-row tile spent in each phase of the fused edge kernel for `layer` on the current
+ * batch: out[0] row-info + P/Q wait, [1] A generation, [2] MMA tail, [3] epilogue pass 1, [4] pass 2 / coordinate
+ * update, [5] A-ring back-pressure (part of [1]), [6] tiles profiled, [7..10] pass-2 sub-phases (wait for the
+ * segment-sum MMA, TMEM load + gate + pack, stage + arrive, readout).  out must hold 16 doubles.  Synchronous. */
+int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, void* stream);
+
 /* Test hook: C[M x N] = A[M x K] . W[N x K]^T + bias through the tcgen05 GEMM kernel (row-major fp32 in / out,
  * converted to operand format internally).  mode = MLCG_PREC_TF32 or MLCG_PREC_BF16; bn = 448 or 256. */
 int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,

@@ -16,7 +16,7 @@ EXPORTS = [
     "mlcg_version", "mlcg_create", "mlcg_destroy", "mlcg_last_error", "mlcg_load_egnn", "mlcg_load_seer",
     "mlcg_set_batch", "mlcg_egnn_forward", "mlcg_noise_init", "mlcg_step", "mlcg_reinject", "mlcg_forward_diffuse",
     "mlcg_decode", "mlcg_sample", "mlcg_seer_inputs", "mlcg_seer_forward", "mlcg_generate", "mlcg_num_edge_tiles",
-    "mlcg_num_edges", "mlcg_kernel_launches", "mlcg_time_edge_kernel", "mlcg_test_gemm",
+    "mlcg_num_edges", "mlcg_kernel_launches", "mlcg_time_edge_kernel", "mlcg_edge_phase_profile", "mlcg_test_gemm",
 ]
 
 
@@ -90,6 +90,7 @@ def load() -> C.CDLL:
     lib.mlcg_kernel_launches.restype = C.c_int64
     lib.mlcg_time_edge_kernel.argtypes = [vp, ci, ci, vp]
     lib.mlcg_time_edge_kernel.restype = cf
+    lib.mlcg_edge_phase_profile.argtypes = [vp, ci, C.POINTER(C.c_double), vp]
     lib.mlcg_test_gemm.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, vp]
     _lib = lib
     return lib

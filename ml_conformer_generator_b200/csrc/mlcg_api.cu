@@ -1,6 +1,8 @@
 // C-ABI of libmlcg_b200.so (see include/mlcg.h).  Host-side orchestration only: weight repacking at load time, batch
 // plan (edge-tile table), kernel sequencing of one EGNN forward / the reverse-diffusion loop / the AdjMatSeer GCN.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -46,6 +48,7 @@ struct LayerW {
   float att_bias = 0.f;
   DevBuf w1ab_op, w2_op, w3_op, w4_op;  // operand-format (tensor-core modes)
   DevBuf bias_pq, wc, wd, wvp, b3p, b4p;  // padded fp32 vectors
+  float h_wc[HP], h_wd[HP], h_wv[HP];     // host copies passed to the edge kernel through the constant bank
 };
 
 struct SeerLayer {
@@ -281,6 +284,9 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
     if ((rc = pad_vec(h, L.wd, L.w1.d + 2 * HID + 1, 2 * HID + 2, HID, HP))) return rc;
     if ((rc = pad_vec(h, L.wvp, L.wv.d, 1, HID, HP))) return rc;
     if ((rc = pad_vec(h, L.bias_pq, L.b1.d, 1, HID, HP, HP, 2 * HP))) return rc;  // [0 | b1]
+    CK(cudaMemcpy(L.h_wc, L.wc.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(L.h_wd, L.wd.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(L.h_wv, L.wvp.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
     if (!L.equiv) {
       if ((rc = pad_vec(h, L.b3p, L.b3.d, 1, HID, HP))) return rc;
       if ((rc = pad_vec(h, L.b4p, L.b4.d, 1, HID, HP))) return rc;
@@ -459,6 +465,13 @@ extern "C" int64_t mlcg_kernel_launches(mlcg_handle* h) { return h ? h->launches
 // ---------------------------------------------------------------------------------------------------------------
 // EGNN forward
 // ---------------------------------------------------------------------------------------------------------------
+// grid of the persistent edge kernel: one CTA per SM (MLCG_EDGE_GRID overrides it for scaling experiments)
+static int edge_grid(mlcg_handle* h) {
+  int g = std::min(h->n_etiles, h->num_sms);
+  if (const char* e = getenv("MLCG_EDGE_GRID")) g = std::max(1, std::min(g, atoi(e)));
+  return g;
+}
+
 static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, float* x_next) {
   EdgeArgs a{};
   a.tiles = h->d_tiles.as<int4>();
@@ -470,18 +483,19 @@ static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, f
   a.x_next = x_next;
   a.w2 = L.w2_op.as<uint8_t>();
   a.n_kc = h->kc448();
-  a.wc = L.wc.as<float>();
-  a.wd = L.wd.as<float>();
-  a.wv = L.wvp.as<float>();
+  memcpy(a.wc, L.h_wc, sizeof(a.wc));
+  memcpy(a.wd, L.h_wd, sizeof(a.wd));
+  memcpy(a.wv, L.h_wv, sizeof(a.wv));
   a.att_bias = L.att_bias;
   a.agg_op = h->agg_op.as<uint8_t>();
   a.agg_chunks = h->kc448();
+  a.prof = nullptr;
   return a;
 }
 
 static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
   const int mode = h->precision, kc = h->kc448();
-  const int grid_e = std::min(h->n_etiles, h->num_sms);
+  const int grid_e = edge_grid(h);
   auto gemm_pq = [&](const LayerW& L) -> cudaError_t {
     GemmArgs a{};
     a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
@@ -897,7 +911,7 @@ extern "C" float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, voi
   cudaStream_t st = (cudaStream_t)stream;
   const LayerW& L = h->layers[layer];
   EdgeArgs ea = edge_args(h, L, h->xa.as<float>(), h->xb.as<float>());
-  const int grid_e = std::min(h->n_etiles, h->num_sms);
+  const int grid_e = edge_grid(h);
   cudaEvent_t e0, e1;
   if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.f;
   if (launch_edge_mode(h->precision, L.equiv, ea, grid_e, st) != cudaSuccess) return -1.f;  // warm-up
@@ -913,6 +927,33 @@ extern "C" float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, voi
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return ms / iters;
+}
+
+// Diagnostics: per-phase cycle counters of the fused edge kernel, averaged over CTAs and tiles.
+// out[0..5] = cycles per tile: row-info + P/Q wait, A generation, MMA tail, pass 1, pass 2, A-ring back-pressure.
+extern "C" int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, void* stream) {
+  if (!h || !out) return MLCG_E_ARG;
+  if (!h->egnn_loaded || !h->batch_set || h->precision == PREC_FP32_SIMT || layer < 0 || layer >= 27)
+    FAIL(MLCG_E_STATE, "edge_phase_profile: needs a tensor-core precision, weights and a batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerW& L = h->layers[layer];
+  const int grid_e = edge_grid(h);
+  DevBuf buf;
+  CK(buf.ensure((size_t)grid_e * 16 * sizeof(long long)));
+  EdgeArgs ea = edge_args(h, L, h->xa.as<float>(), h->xb.as<float>());
+  ea.prof = buf.as<long long>();
+  CK(launch_edge_mode(h->precision, L.equiv, ea, grid_e, st));
+  h->launches++;
+  std::vector<long long> host((size_t)grid_e * 16);
+  CK(cudaMemcpyAsync(host.data(), buf.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  buf.release();
+  double acc[16] = {0};
+  for (int b = 0; b < grid_e; ++b)
+    for (int k = 0; k < 16; ++k) acc[k] += (double)host[(size_t)b * 16 + k];
+  const double tiles = acc[6] > 0 ? acc[6] : 1.0;
+  for (int k = 0; k < 16; ++k) out[k] = (k == 6) ? acc[k] : acc[k] / tiles;
+  return MLCG_OK;
 }
 
 extern "C" int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,

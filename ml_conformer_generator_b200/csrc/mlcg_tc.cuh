@@ -193,23 +193,41 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 // fused edge kernel
 // ---------------------------------------------------------------------------------------------------------------
+// One CTA per SM, persistent over a contiguous range of 128-row tiles.  A tile = up to EDGE_MAXG target atoms i of
+// one molecule x all their neighbours j != i (rows ordered i-major, j ascending).
+//
+//   warp 0      bulk-copy producer: per tile P rows (ng) + Q rows (molecule change only), per K chunk two 28 KB
+//               half-blocks of W2 into a 3-slot ring
+//   warp 1      tcgen05.mma issuer, TS mode: A operand read from TMEM, B (W2) from shared memory, D in TMEM
+//   warps 2-17  compute: 4 threads per tile row (= TMEM lane).  A generation writes SiLU(P_i+Q_j+d2*wc+d02*wd)
+//               straight into a 2-stage A ring in TMEM (columns 448..511) with tcgen05.st -- the A operand never
+//               touches shared memory, which is the bandwidth-critical resource of this kernel (the SS-mode version
+//               spent ~200 KB of shared-memory traffic per K chunk and ran at the 128 B/clk crossbar limit).
+//               Epilogue: pass 1 SiLU + gate dot (thread-local per row), pass 2 gate + segment sum over j.
+// The per-layer vectors wc, wd, wv live in the constant bank (kernel parameters): warp-uniform operands that cost no
+// shared-memory bandwidth.
 constexpr int EDGE_MAXG = 12;          // max target nodes (groups) per 128-row tile
 constexpr int EDGE_MAXN = 39;          // max atoms per molecule (reference config.py MAX_N_NODES)
 constexpr int EDGE_WSLOT = 224 * CHUNK_BYTES;  // 28,672 B: one (K chunk, N half) block of W2
 constexpr int EDGE_NW = 3;             // W ring slots
-constexpr int EDGE_NA = 2;             // A ring stages (also the epilogue's transposition scratch)
+constexpr int EDGE_NA = 2;             // A ring stages (TMEM columns 448..479 and 480..511)
+constexpr int EDGE_ACOL = 448;         // first TMEM column of the A ring
 constexpr int EDGE_QPITCH = 452;       // floats; 1808 B rows -> conflict-free LDS.128 across consecutive j
-constexpr int EDGE_THREADS = 320;      // warp 0 producer, warp 1 MMA, warps 2..9 compute
+constexpr int EDGE_CT = 512;           // compute threads (16 warps)
+constexpr int EDGE_THREADS = 64 + EDGE_CT;  // warp 0 producer, warp 1 MMA, warps 2..17 compute
 
 struct EdgeSmem {
   static constexpr int W_OFF = 0;
-  static constexpr int A_OFF = W_OFF + EDGE_NW * EDGE_WSLOT;
-  static constexpr int Q_OFF = A_OFF + EDGE_NA * A_CHUNK_BYTES;
+  static constexpr int SCR_OFF = W_OFF + EDGE_NW * EDGE_WSLOT;   // 32 KB epilogue staging for the segment sum
+  static constexpr int SEL_OFF = SCR_OFF + 2 * A_CHUNK_BYTES;   // 4 KB group selector S[16 x 128] (bf16, K-major SW128)
+  static constexpr int Q_OFF = SEL_OFF + 4096;
   static constexpr int P_OFF = Q_OFF + ((EDGE_MAXN * EDGE_QPITCH * 4 + 127) / 128) * 128;
-  static constexpr int VEC_OFF = P_OFF + EDGE_MAXG * HP * 4;   // wc, wd, wv
-  static constexpr int DOT_OFF = VEC_OFF + 3 * HP * 4;          // [2][128] partial dots
-  static constexpr int TRS_OFF = DOT_OFF + 2 * TILE_M * 4;      // [128][3] coordinate messages
-  static constexpr int BAR_OFF = TRS_OFF + TILE_M * 3 * 4;
+  static constexpr int DOT_OFF = P_OFF + EDGE_MAXG * EDGE_QPITCH * 4;  // [4][128] partial dots
+  static constexpr int TRS_OFF = DOT_OFF + 4 * TILE_M * 4;      // [128][3] coordinate messages
+  static constexpr int RID_OFF = TRS_OFF + TILE_M * 3 * 4;      // [128] float2 (d2, d0^2)
+  static constexpr int RIG_OFF = RID_OFF + TILE_M * 8;          // [128] int  g | j<<8 | valid<<16
+  static constexpr int PROF_OFF = RIG_OFF + TILE_M * 4;         // 16 x int64 phase counters (diagnostics)
+  static constexpr int BAR_OFF = PROF_OFF + 128;
   static constexpr int TOTAL = BAR_OFF + 256;
   static constexpr int ALLOC = TOTAL + 1024;
 };
@@ -224,29 +242,53 @@ struct EdgeArgs {
   float* x_next;       // equivariant update output
   const uint8_t* w2;   // packed second-layer weights [n_kc][448 x 128 B] (bias folded into K column 420)
   int n_kc;
-  const float* wc;     // [448] first-layer column for d2 (W1[:,840])
-  const float* wd;     // [448] first-layer column for d0^2 (W1[:,841])
-  const float* wv;     // [448] attention vector (GCL) or coordinate head (equivariant update)
   float att_bias;
   uint8_t* agg_op;     // GCL: neighbour aggregate, operand format
   int agg_chunks;
+  long long* prof;     // optional [grid][16] per-CTA phase cycle counters (diagnostics), or nullptr
+  float wc[HP];        // first-layer column for d2 (W1[:,840]), zero padded          } constant bank
+  float wd[HP];        // first-layer column for d0^2 (W1[:,841])                      }
+  float wv[HP];        // attention vector (GCL) or coordinate head (equivariant)      }
 };
 
+template <int kMode>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kMode == PREC_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 template <int kMode, bool kEquiv>
-__global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
+__global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_constant__ EdgeArgs p) {
   constexpr bool kFast = (kMode == PREC_BF16);
-  constexpr int EPC = epc(kMode), EPP = epp(kMode);
+  constexpr int EPC = epc(kMode);
+  constexpr int ELEMS = EPC / 4;  // K elements per thread per chunk (16 bf16 / 8 tf32) = 8 TMEM columns
+  constexpr bool kSegMma = (kMode == PREC_BF16) && !kEquiv;  // neighbour sum on the tensor core (bf16 mode)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   float* Qs = reinterpret_cast<float*>(gbase + EdgeSmem::Q_OFF);
   float* Ps = reinterpret_cast<float*>(gbase + EdgeSmem::P_OFF);
-  float* wc_s = reinterpret_cast<float*>(gbase + EdgeSmem::VEC_OFF);
-  float* wd_s = wc_s + HP;
-  float* wv_s = wd_s + HP;
   float* dots = reinterpret_cast<float*>(gbase + EdgeSmem::DOT_OFF);
   float* trs = reinterpret_cast<float*>(gbase + EdgeSmem::TRS_OFF);
-  uint8_t* scratch = gbase + EdgeSmem::A_OFF;
+  float2* ri_d = reinterpret_cast<float2*>(gbase + EdgeSmem::RID_OFF);
+  int* ri_gj = reinterpret_cast<int*>(gbase + EdgeSmem::RIG_OFF);
+  uint8_t* scratch = gbase + EdgeSmem::SCR_OFF;
   const uint32_t bar0 = base + EdgeSmem::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
   auto w_empty = [&](int s) { return bar0 + 8u * (EDGE_NW + s); };
@@ -256,7 +298,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
   const uint32_t pq_empty = pq_full + 8u;
   const uint32_t d_full = pq_full + 16u;
   const uint32_t d_empty = pq_full + 24u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NW + 2 * EDGE_NA + 4));
+  const uint32_t e_full = pq_full + 32u;   // gated messages of one 128-channel block staged (compute -> MMA)
+  const uint32_t e_done = pq_full + 40u;   // segment-sum MMA of that block complete (MMA -> compute)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NW + 2 * EDGE_NA + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
@@ -268,21 +312,18 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
       mbar_init(w_empty(s), 1);
     }
     for (int s = 0; s < EDGE_NA; ++s) {
-      mbar_init(a_full(s), 256);
+      mbar_init(a_full(s), EDGE_CT / 32);
       mbar_init(a_empty(s), 1);
     }
     mbar_init(pq_full, 1);
-    mbar_init(pq_empty, 256);
+    mbar_init(pq_empty, EDGE_CT / 32);
     mbar_init(d_full, 1);
-    mbar_init(d_empty, 256);
+    mbar_init(d_empty, EDGE_CT / 32);
+    mbar_init(e_full, EDGE_CT / 32);
+    mbar_init(e_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
-  for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) {
-    wc_s[i] = p.wc[i];
-    wd_s[i] = p.wd[i];
-    wv_s[i] = p.wv[i];
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,7 +342,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
         const bool newmol = (mol != prev_mol);
         mbar_arrive_expect_tx(pq_full, (uint32_t)((ng + (newmol ? n : 0)) * HP * 4));
         for (int g = 0; g < ng; ++g)
-          bulk_g2s(base + EdgeSmem::P_OFF + g * HP * 4, p.pq + (size_t)(node0 + i0 + g) * (2 * HP), HP * 4, pq_full);
+          bulk_g2s(base + EdgeSmem::P_OFF + g * EDGE_QPITCH * 4, p.pq + (size_t)(node0 + i0 + g) * (2 * HP), HP * 4, pq_full);
         if (newmol)
           for (int j = 0; j < n; ++j)
             bulk_g2s(base + EdgeSmem::Q_OFF + j * EDGE_QPITCH * 4, p.pq + (size_t)(node0 + j) * (2 * HP) + HP, HP * 4,
@@ -320,7 +361,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== tcgen05.mma issuer =====================
+    // ===================== tcgen05.mma issuer (A from TMEM, B from shared memory) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, TILE_M, 224);
       uint32_t wi = 0, ai = 0;
@@ -330,7 +371,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
         for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
           const int as = ai % EDGE_NA;
           mbar_wait(a_full(as), (ai / EDGE_NA) & 1);
-          const uint64_t adesc = umma_desc_sw128(base + EdgeSmem::A_OFF + as * A_CHUNK_BYTES);
+          const uint32_t a_tmem = tmem_base + EDGE_ACOL + as * 32;
           for (int nh = 0; nh < 2; ++nh, ++wi) {
             const int ws = wi % EDGE_NW;
             mbar_wait(w_full(ws), (wi / EDGE_NW) & 1);
@@ -338,120 +379,170 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
             const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::W_OFF + ws * EDGE_WSLOT);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma<kMode>(tmem_base + nh * 224, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+              umma_ts<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
             umma_commit(w_empty(ws));
           }
           umma_commit(a_empty(as));
         }
         umma_commit(d_full);
+        if constexpr (kSegMma) {
+          // segment sum over neighbours on the tensor core: D2[128 channels x 16 groups] = E^T . S^T per 128-channel
+          // block; E (gated messages, bf16) is staged row-major = MN-major A operand, S is the 0/1 group selector.
+          constexpr uint32_t idesc2 = umma_idesc(1, TILE_M, 16) | (1u << 15);  // A is MN-major
+          for (int cb = 0; cb < 4; ++cb) {
+            mbar_wait(e_full, (uint32_t)((it * 4 + cb) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t adesc = umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + ks * 2048, A_CHUNK_BYTES);
+              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (ks >> 2) * 2048) + 2 * (ks & 3);
+              umma<PREC_BF16>(tmem_base + EDGE_ACOL + (cb & 1) * 16, adesc, bdesc, idesc2, ks != 0);
+            }
+            umma_commit(e_done);
+          }
+        }
       }
     }
   } else {
     // ===================== compute warps: A generation + epilogue =====================
-    const int ct = threadIdx.x - 64;       // 0..255
-    const int cw = ct >> 5;                // 0..7
+    const int ct = threadIdx.x - 64;       // 0..511
+    const int cw = ct >> 5;                // 0..15
     const int q = warp & 3;                // TMEM lane quarter this warp may access
-    const int hf = cw >> 2;                // which half of the K pieces / output columns
+    const int qq = cw >> 2;                // quarter of each K chunk (A generation) / of the output columns (epilogue)
     const int r = q * 32 + lane;           // tile row = TMEM lane
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t ai = 0;
+    long long* pacc = reinterpret_cast<long long*>(gbase + EdgeSmem::PROF_OFF);  // only thread ct == 0 touches it
+    const bool profiling = (p.prof != nullptr) && (ct == 0);
+    if (profiling)
+      for (int k = 0; k < 16; ++k) pacc[k] = 0;
     for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+      long long c0 = profiling ? clock64() : 0;
       const int4 ti = p.tiles[t];
       const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
       const int nm1 = max(n - 1, 1);
       const int nrows = ng * (n - 1);
       const int node0 = p.node_off[mol];
-      const bool valid = r < nrows;
-      const int g = valid ? r / nm1 : 0;
-      const int jj = valid ? r - g * nm1 : 0;
-      const int i = i0 + g;
-      const int j = valid ? jj + (jj >= i ? 1 : 0) : 0;
-      float d2, d02, ux, uy, uz;
-      {
+      // ---- per-row metadata (one thread per row) ----
+      if (ct < TILE_M) {
+        const int rr = ct;
+        const bool rvalid = rr < nrows;
+        const int g = rvalid ? rr / nm1 : 0;
+        const int jj = rvalid ? rr - g * nm1 : 0;
+        const int i = i0 + g;
+        const int j = rvalid ? jj + (jj >= i ? 1 : 0) : 0;
         const float* xi = p.x_cur + (size_t)(node0 + i) * 3;
         const float* xj = p.x_cur + (size_t)(node0 + j) * 3;
         const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-        d2 = dx * dx + dy * dy + dz * dz;
-        const float inv = 1.0f / sqrtf(d2 + 1e-8f);
-        ux = dx * inv; uy = dy * inv; uz = dz * inv;
+        const float d2 = dx * dx + dy * dy + dz * dz;
         const float* yi = p.x0 + (size_t)(node0 + i) * 3;
         const float* yj = p.x0 + (size_t)(node0 + j) * 3;
         const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
-        d02 = ex * ex + ey * ey + ez * ez;
+        ri_d[rr] = make_float2(d2, ex * ex + ey * ey + ez * ez);
+        ri_gj[rr] = g | (j << 8) | (rvalid ? 0x10000 : 0);
+        if constexpr (kEquiv) {
+          const float inv = 1.0f / sqrtf(d2 + 1e-8f);
+          trs[rr * 3 + 0] = dx * inv; trs[rr * 3 + 1] = dy * inv; trs[rr * 3 + 2] = dz * inv;
+        }
       }
+      if constexpr (kSegMma) {
+        // S[g][k] = 1 if tile row k belongs to target node g: thread = (group g, 16-byte piece of 8 rows)
+        if (ct < 256) {
+          const int g = ct >> 4, piece = ct & 15;
+          const int lo_k = g * nm1, hi_k = min(lo_k + n - 1, nrows);  // rows [lo_k, hi_k) belong to group g
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = piece * 8 + 2 * e;
+            const uint32_t lo = (k >= lo_k && k < hi_k) ? 0x3f80u : 0u;          // bf16 1.0
+            const uint32_t hi = (k + 1 >= lo_k && k + 1 < hi_k) ? 0x3f80u : 0u;
+            w[e] = lo | (hi << 16);
+          }
+          *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      named_bar_sync(1, EDGE_CT);
+      const int info = ri_gj[r];
+      const bool valid = (info & 0x10000) != 0;
+      const float2 rd = ri_d[r];
+      const float* Prow = Ps + (info & 0xff) * EDGE_QPITCH + qq * ELEMS;         // invalid rows read row 0 (finite)
+      const float* Qrow = Qs + ((info >> 8) & 0xff) * EDGE_QPITCH + qq * ELEMS;
       mbar_wait(pq_full, (uint32_t)(it & 1));
-      const float* Prow = Ps + g * HP;
-      const float* Qrow = Qs + j * EDGE_QPITCH;
+      if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
-      // ---- A generation: SiLU(P_i + Q_j + d2*wc + d02*wd) -> swizzled operand chunks ----
+      // ---- A generation: SiLU(P_i + Q_j + d2*wc + d02*wd) -> TMEM A ring ----
+#pragma unroll 1
       for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
         const int as = ai % EDGE_NA;
-        mbar_wait(a_empty(as), ((ai / EDGE_NA) & 1) ^ 1u);
-        uint8_t* stage = gbase + EdgeSmem::A_OFF + as * A_CHUNK_BYTES;
+        const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
+        float a[ELEMS];
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) {
-          const int piece = hf * 4 + pp;
-          const int k0 = kc * EPC + piece * EPP;
-          float a[EPP];
-#pragma unroll
-          for (int e = 0; e < EPP; e += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(Prow + k0 + e);
-            const float4 qv = *reinterpret_cast<const float4*>(Qrow + k0 + e);
-            const float4 cv = *reinterpret_cast<const float4*>(wc_s + k0 + e);
-            const float4 dv = *reinterpret_cast<const float4*>(wd_s + k0 + e);
-            a[e + 0] = silu<kFast>(fmaf(d02, dv.x, fmaf(d2, cv.x, pv.x + qv.x)));
-            a[e + 1] = silu<kFast>(fmaf(d02, dv.y, fmaf(d2, cv.y, pv.y + qv.y)));
-            a[e + 2] = silu<kFast>(fmaf(d02, dv.z, fmaf(d2, cv.z, pv.z + qv.z)));
-            a[e + 3] = silu<kFast>(fmaf(d02, dv.w, fmaf(d2, cv.w, pv.w + qv.w)));
-          }
-          constexpr int BE = BIAS_COL % EPP;
-          if (k0 == BIAS_COL - BE) a[BE] = 1.0f;  // constant-1 column carrying b2
-          uint4 w;
-          if constexpr (kMode == PREC_BF16) {
-            w.x = pack_bf16x2(a[0], a[1]); w.y = pack_bf16x2(a[2], a[3]);
-            w.z = pack_bf16x2(a[4], a[5]); w.w = pack_bf16x2(a[6], a[7]);
-          } else {
-            w.x = f32_to_tf32(a[0]); w.y = f32_to_tf32(a[1]); w.z = f32_to_tf32(a[2]); w.w = f32_to_tf32(a[3]);
-          }
-          *reinterpret_cast<uint4*>(stage + sw128_offset(r, piece)) = w;
+        for (int e = 0; e < ELEMS; e += 4) {
+          const float4 pv = *reinterpret_cast<const float4*>(Prow + kc * EPC + e);
+          const float4 qv = *reinterpret_cast<const float4*>(Qrow + kc * EPC + e);
+          a[e + 0] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 0], fmaf(rd.x, p.wc[k0 + e + 0], pv.x + qv.x)));
+          a[e + 1] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 1], fmaf(rd.x, p.wc[k0 + e + 1], pv.y + qv.y)));
+          a[e + 2] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 2], fmaf(rd.x, p.wc[k0 + e + 2], pv.z + qv.z)));
+          a[e + 3] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 3], fmaf(rd.x, p.wc[k0 + e + 3], pv.w + qv.w)));
         }
-        fence_proxy_async();
-        mbar_arrive(a_full(as));
+        // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416, both modes)
+        if (k0 == BIAS_COL - 4) a[4] = 1.0f;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if constexpr (kMode == PREC_BF16) w[i] = pack_bf16x2(a[2 * i], a[2 * i + 1]);
+          else w[i] = f32_to_tf32(a[i]);
+        }
+        long long cw0 = profiling ? clock64() : 0;
+        mbar_wait(a_empty(as), ((ai / EDGE_NA) & 1) ^ 1u);
+        if (profiling) pacc[5] += clock64() - cw0;  // A-ring back-pressure (MMA / weight stream slower than A generation)
+        tc_fence_after();
+        tmem_st8(trow + EDGE_ACOL + as * 32 + qq * 8, w);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(as));  // one arrival per warp
       }
-      mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
+      if (profiling) { long long c = clock64(); pacc[1] += c - c0; c0 = c; }  // A generation (incl. back-pressure)
 
-      // ---- epilogue ----
+      // ---- epilogue pass 1: m = SiLU(D) (written back to TMEM for GCL), partial dot with the gate / coord vector ----
       mbar_wait(d_full, (uint32_t)(it & 1));
       tc_fence_after();
-      float dot = 0.f;
+      if (profiling) { long long c = clock64(); pacc[2] += c - c0; c0 = c; }  // MMA tail
+      float dotp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
       for (int ch = 0; ch < 7; ++ch) {
-        const int col0 = hf * 224 + ch * 32;
-        float v[32];
-        tmem_ld32(trow + col0, v);
+        const int col0 = qq * 112 + ch * 16;  // warp-uniform
+        float v[16];
+        tmem_ld16(trow + col0, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 wv4 = *reinterpret_cast<const float4*>(wv_s + col0 + e);
-          dot = fmaf(silu<kFast>(v[e + 0]), wv4.x, dot);
-          dot = fmaf(silu<kFast>(v[e + 1]), wv4.y, dot);
-          dot = fmaf(silu<kFast>(v[e + 2]), wv4.z, dot);
-          dot = fmaf(silu<kFast>(v[e + 3]), wv4.w, dot);
+        for (int e = 0; e < 16; e += 4) {
+          v[e + 0] = silu<kFast>(v[e + 0]); v[e + 1] = silu<kFast>(v[e + 1]);
+          v[e + 2] = silu<kFast>(v[e + 2]); v[e + 3] = silu<kFast>(v[e + 3]);
+          dotp[0] = fmaf(v[e + 0], p.wv[col0 + e + 0], dotp[0]); dotp[1] = fmaf(v[e + 1], p.wv[col0 + e + 1], dotp[1]);
+          dotp[2] = fmaf(v[e + 2], p.wv[col0 + e + 2], dotp[2]); dotp[3] = fmaf(v[e + 3], p.wv[col0 + e + 3], dotp[3]);
         }
+        if constexpr (!kEquiv) tmem_st16(trow + col0, v);
       }
-      dots[hf * TILE_M + r] = dot;
-      named_bar_sync(1, 256);
-      const float full_dot = dots[r] + dots[TILE_M + r];
+      dots[qq * TILE_M + r] = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
+      if constexpr (!kEquiv) tmem_wait_st();
+      named_bar_sync(1, EDGE_CT);
+      if (profiling) { long long c = clock64(); pacc[3] += c - c0; c0 = c; }  // pass 1
+      const float full_dot = (dots[r] + dots[TILE_M + r]) + (dots[2 * TILE_M + r] + dots[3 * TILE_M + r]);
       if constexpr (kEquiv) {
         // x_i += sum_j unit_ij * phi_ij / 100   (reference egnn.py:124-134)
         tc_fence_before();
-        mbar_arrive(d_empty);
-        if (hf == 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
+        if (qq == 0) {
           const float phi = valid ? full_dot : 0.f;
-          trs[r * 3 + 0] = ux * phi;
-          trs[r * 3 + 1] = uy * phi;
-          trs[r * 3 + 2] = uz * phi;
+          trs[r * 3 + 0] *= phi; trs[r * 3 + 1] *= phi; trs[r * 3 + 2] *= phi;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, EDGE_CT);
         if (ct < ng * 3) {
           const int gg = ct / 3, c = ct - gg * 3;
           float s = 0.f;
@@ -459,44 +550,129 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const EdgeArgs p) {
           const size_t idx = (size_t)(node0 + i0 + gg) * 3 + c;
           p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, EDGE_CT);
       } else {
         // e_ij = m_ij * sigmoid(w_a.m_ij + b_a); agg_i = sum_j e_ij / 100   (reference egnn.py:48-51, 59-64)
         const float gate = valid ? sigmoid_acc(full_dot + p.att_bias) : 0.f;
+        if constexpr (kSegMma) {
+          // thread (row r, qq) stages channels cb*128 + qq*32 .. +31 of each 128-channel block cb as bf16
+          uint32_t ew[16];
+          auto load_gate_pack = [&](int cb) {
+            if (cb * 128 + qq * 32 < HP) {
+              float v[32];
+              tmem_ld32(trow + cb * 128 + qq * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ew[i] = pack_bf16x2(v[2 * i] * gate, v[2 * i + 1] * gate);
+            }
+          };
+          // D2 readout: lane = channel cb*128 + r, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
+          const int rd_piece = (r >> 3) & 7;  // 16-byte piece of this thread's channel inside its 64-channel chunk
+          auto readout = [&](int cb) {
+            float v[16];
+            tmem_ld16(trow + EDGE_ACOL + (cb & 1) * 16, v);
+            tmem_wait_ld();
+            const int ch = cb * 128 + r;
+            if (ch < HP) {
+              uint8_t* cbase = p.agg_op + (size_t)(ch >> 6) * A_CHUNK_BYTES + (ch & 7) * 2;
+#pragma unroll
+              for (int gi = 0; gi < 3; ++gi) {
+                const int g = qq + 4 * gi;
+                if (g < ng) {
+                  const int node = node0 + i0 + g;
+                  uint8_t* dst = cbase + (size_t)(node >> 7) * p.agg_chunks * A_CHUNK_BYTES + (node & 127) * 128 +
+                                 ((rd_piece ^ (node & 7)) << 4);
+                  // select v[g] without dynamic register indexing
+                  const float val = (gi == 0) ? (qq == 0 ? v[0] : qq == 1 ? v[1] : qq == 2 ? v[2] : v[3])
+                                  : (gi == 1) ? (qq == 0 ? v[4] : qq == 1 ? v[5] : qq == 2 ? v[6] : v[7])
+                                              : (qq == 0 ? v[8] : qq == 1 ? v[9] : qq == 2 ? v[10] : v[11]);
+                  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
+                }
+              }
+            }
+            tc_fence_before();
+          };
+          long long s0 = profiling ? clock64() : 0;
+          load_gate_pack(0);
+          if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            if (cb > 0) {
+              mbar_wait(e_done, (uint32_t)((it * 4 + cb - 1) & 1));  // staging buffer free, D2(cb-1) ready
+              tc_fence_after();
+            }
+            if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }  // wait for the segment-sum MMA
+            if (cb * 128 + qq * 32 < HP) {
+              uint8_t* dst = scratch + (qq >> 1) * A_CHUNK_BYTES;
+#pragma unroll
+              for (int pi = 0; pi < 4; ++pi)
+                *reinterpret_cast<uint4*>(dst + sw128_offset(r, (qq & 1) * 4 + pi)) =
+                    make_uint4(ew[4 * pi], ew[4 * pi + 1], ew[4 * pi + 2], ew[4 * pi + 3]);
+            }
+            fence_proxy_async();
+            if (cb == 3) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive(e_full);
+              if (cb == 3) mbar_arrive(d_empty);  // all reads of D for this tile are complete
+            }
+            if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // stage + fence + arrive
+            if (cb < 3) load_gate_pack(cb + 1);
+            if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }   // TMEM load + gate + pack
+            if (cb > 0) readout(cb - 1);
+            if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }  // D2 readout + stores
+          }
+          mbar_wait(e_done, (uint32_t)((it * 4 + 3) & 1));
+          tc_fence_after();
+          if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
+          readout(3);
+          if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
+        } else {
+#pragma unroll 1
         for (int ch = 0; ch < 7; ++ch) {
-          const int col0 = hf * 224 + ch * 32;
-          float v[32];
-          tmem_ld32(trow + col0, v);
+          const int col0 = qq * 112 + ch * 16;
+          float v[16];
+          tmem_ld16(trow + col0, v);
           tmem_wait_ld();
           if (ch == 6) {
             tc_fence_before();
-            mbar_arrive(d_empty);  // last TMEM read of this tile is complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty);  // last TMEM read of this tile is complete
           }
-          named_bar_sync(1, 256);  // previous chunk's readers are done with the scratch
+          named_bar_sync(1, EDGE_CT);  // previous chunk's readers are done with the scratch
+          // staging: two 16 KB halves of [128 rows x 32 fp32]; quarter qq lands in half qq>>1, columns (qq&1)*16..
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
+          for (int e = 0; e < 16; e += 4) {
             float4 o;
-            o.x = silu<kFast>(v[e + 0]) * gate;
-            o.y = silu<kFast>(v[e + 1]) * gate;
-            o.z = silu<kFast>(v[e + 2]) * gate;
-            o.w = silu<kFast>(v[e + 3]) * gate;
-            *reinterpret_cast<float4*>(scratch + hf * A_CHUNK_BYTES + sw128_offset(r, e >> 2)) = o;
+            o.x = v[e + 0] * gate; o.y = v[e + 1] * gate; o.z = v[e + 2] * gate; o.w = v[e + 3] * gate;
+            *reinterpret_cast<float4*>(scratch + (qq >> 1) * A_CHUNK_BYTES + sw128_offset(r, (qq & 1) * 4 + (e >> 2))) = o;
           }
-          named_bar_sync(1, 256);
-          // segment sum over neighbours j in ascending order (the CPU reference's scatter_add order)
-          for (int pr = cw; pr < 2 * ng; pr += 8) {
+          named_bar_sync(1, EDGE_CT);
+          // segment sum over the neighbours of each target node (4 interleaved partial sums, fixed order)
+          for (int pr = cw; pr < 2 * ng; pr += 16) {
             const int hh = pr & 1, gg = pr >> 1;
             const uint8_t* src = scratch + hh * A_CHUNK_BYTES + (lane & 3) * 4;
-            float s = 0.f;
-            const int r0 = gg * nm1;
-            for (int e = 0; e < n - 1; ++e)
-              s += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e, lane >> 2));
-            op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, hh * 224 + ch * 32 + lane, s / 100.0f);
+            const int r0 = gg * nm1, cnt = n - 1;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int e = 0;
+            for (; e + 3 < cnt; e += 4) {
+              s0 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e + 0, lane >> 2));
+              s1 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e + 1, lane >> 2));
+              s2 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e + 2, lane >> 2));
+              s3 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e + 3, lane >> 2));
+            }
+            for (; e < cnt; ++e) s0 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e, lane >> 2));
+            const int col = (2 * hh + (lane >> 4)) * 112 + ch * 16 + (lane & 15);
+            op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, col, ((s0 + s1) + (s2 + s3)) / 100.0f);
           }
         }
-        named_bar_sync(1, 256);  // scratch (= A ring) is free again before the next tile's A generation
+        }
+        named_bar_sync(1, EDGE_CT);  // staging is free again
       }
+      if (profiling) { long long c = clock64(); pacc[4] += c - c0; pacc[6] += 1; }  // pass 2 / coordinate update
     }
+    if (profiling)
+      for (int k = 0; k < 16; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = pacc[k];
   }
   tc_fence_before();
   __syncthreads();

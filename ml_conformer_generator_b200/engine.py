@@ -213,6 +213,13 @@ class Engine:
     def time_edge_kernel(self, layer: int = 0, iters: int = 10) -> float:
         return float(self.lib.mlcg_time_edge_kernel(self.h, layer, iters, self._stream()))
 
+    def edge_phase_profile(self, layer: int = 0):
+        out = (C.c_double * 16)()
+        self._check(self.lib.mlcg_edge_phase_profile(self.h, layer, out, self._stream()), "edge_phase_profile")
+        names = ["rowinfo_pq_wait", "a_gen", "mma_tail", "pass1", "pass2", "a_ring_backpressure", "tiles",
+                 "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout"]
+        return {n: float(out[i]) for i, n in enumerate(names)}
+
     def test_gemm(self, mode: str, bn: int, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
         a = a.to(self.device, torch.float32).contiguous()
         w = w.to(self.device, torch.float32).contiguous()
