@@ -184,5 +184,48 @@ def main():
     save("seer", elements=el, dist_mat=dm, adj_mat=am, logits=logits, bonds=bonds, sizes=sizes)
 
 
+
+
+@torch.no_grad()
+def host_fixtures():
+    """Golden vectors for the host-side tensor helpers (reference utils/mol_utils.py), incl. the demo molecules."""
+    load_reference()
+    from mlconfgen.utils import mol_utils as R
+    from ml_conformer_generator_b200.mol_utils import read_mol_heavy_atoms
+    out = {}
+    demo = "/root/reference/assets/demo_files/"
+    for name in ("ceyyag", "yibfeu", "frag_yibfeu"):
+        sym, xyz = read_mol_heavy_atoms(demo + name + ".mol")
+        out[name + "_xyz"] = xyz
+        out[name + "_symbols"] = np.array(sym)
+        centred = xyz - torch.mean(xyz, dim=0)
+        ctx, rot = R.get_context_shape(centred)
+        out[name + "_context"] = ctx
+        out[name + "_rotated"] = rot
+    # inertial fragment matching helpers (fragment expressed in the yibfeu centre-of-mass frame)
+    yib = out["yibfeu_xyz"]
+    ff_x = out["frag_yibfeu_xyz"] - yib.mean(dim=0)
+    norms = {k: torch.tensor(v) for k, v in CONTEXT_NORMS.items()}
+    n_nodes = torch.tensor([21, 25, 23, 22])
+    nm, em, fctx, shift, rot = R.ifm_prepare_gen_fragment_context(
+        fixed_fragment_x=ff_x, reference_context=out["yibfeu_context"], context_norms=norms, n_nodes=n_nodes,
+        max_n_nodes=25, min_n_nodes=21, device=torch.device("cpu"))
+    g = torch.Generator().manual_seed(5)
+    xg = torch.randn(4, 17, 3, generator=g)
+    hg = torch.nn.functional.one_hot(torch.randint(0, 7, (4, 17), generator=g), 8)
+    inv = R.inverse_coord_transform(xg, shift, rot)
+    ff_h = torch.nn.functional.one_hot(torch.tensor([6, 6, 0, 0, 0, 0, 0, 0]), 8)
+    zk, fm = R.ifm_prepare_fragments_for_merge(ff_x, ff_h, inv, hg, torch.device("cpu"), 25)
+    out.update(ifm_ff_x=ff_x, ifm_n_nodes=n_nodes, ifm_node_mask=nm, ifm_edge_mask=em, ifm_context=fctx, ifm_shift=shift,
+               ifm_rotation=rot, ifm_xg=xg, ifm_hg=hg, ifm_inv=inv, ifm_ff_h=ff_h, ifm_z_known=zk, ifm_fixed_mask=fm)
+    torch.manual_seed(123)
+    nm2, em2, ctx2 = R.prepare_edm_input(6, out["ceyyag_context"], norms, 15, 19, torch.device("cpu"))
+    out.update(edm_in_node_mask=nm2, edm_in_edge_mask=em2, edm_in_context=ctx2)
+    save("host_utils", **out)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--host-only" not in sys.argv:
+        main()
+    host_fixtures()

@@ -9,3 +9,4 @@ run seer "seer_golden"
 run gemm "tc_gemm"
 run tf32 "tf32 and not gemm and not seer"
 run bf16 "bf16 and not gemm"
+timeout 900 python -m pytest tests/test_gpu_dropin.py -q -m gpu --timeout=600 > gpurun_out/t_dropin.log 2>&1; echo "dropin exit $?"; tail -5 gpurun_out/t_dropin.log
