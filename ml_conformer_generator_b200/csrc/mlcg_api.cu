@@ -135,11 +135,11 @@ static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
-        cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv>, cudaFuncAttributeMaxDynamicSharedMemorySize, EdgeSmem::ALLOC);
+        cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv>, cudaFuncAttributeMaxDynamicSharedMemorySize, EdgeSmemT<kMode>::ALLOC);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_tc_edge<kMode, kEquiv><<<grid, EDGE_THREADS, EdgeSmem::ALLOC, st>>>(a);
+  k_tc_edge<kMode, kEquiv><<<grid, EDGE_THREADS, EdgeSmemT<kMode>::ALLOC, st>>>(a);
   return cudaGetLastError();
 }
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
@@ -236,9 +236,9 @@ static int need(mlcg_handle* h, std::map<std::string, Wt>& m, const std::string&
   return MLCG_OK;
 }
 static int pad_vec(mlcg_handle* h, DevBuf& dst, const float* src, int stride, int n_real, int n_pad, int dst_off = 0,
-                   int alloc = -1) {
+                   int alloc = -1, float scale = 1.0f) {
   CK(dst.ensure((size_t)(alloc < 0 ? n_pad : alloc) * sizeof(float)));
-  k_pad_vector<<<(n_pad + 127) / 128, 128>>>(src, stride, n_real, dst.as<float>() + dst_off, n_pad);
+  k_pad_vector<<<(n_pad + 127) / 128, 128>>>(src, stride, n_real, dst.as<float>() + dst_off, n_pad, scale);
   KCHECK();
   return MLCG_OK;
 }
@@ -256,6 +256,9 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
   if ((rc = need(h, m, p + "embedding_out.bias", IN_NF, 1, &h->b_out))) return rc;
   const int mode = h->precision;
   const int kc = h->kc448();
+  // bf16 fast mode evaluates SiLU as h + h*tanh(h) with h = x/2: the exact factor 1/2 is folded into the packed first
+  // and second edge-layer weights, their biases and the distance columns (tensor-core path only).
+  const float es = (mode == PREC_BF16) ? 0.5f : 1.0f;
   for (int l = 0; l < 27; ++l) {
     LayerW& L = h->layers[l];
     const int blk = l / 3, sub = l % 3;
@@ -280,10 +283,10 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       CK(cudaMemcpy(&L.att_bias, ab.d, sizeof(float), cudaMemcpyDeviceToHost));
     }
     // padded vectors (all modes)
-    if ((rc = pad_vec(h, L.wc, L.w1.d + 2 * HID, 2 * HID + 2, HID, HP))) return rc;
-    if ((rc = pad_vec(h, L.wd, L.w1.d + 2 * HID + 1, 2 * HID + 2, HID, HP))) return rc;
+    if ((rc = pad_vec(h, L.wc, L.w1.d + 2 * HID, 2 * HID + 2, HID, HP, 0, -1, es))) return rc;
+    if ((rc = pad_vec(h, L.wd, L.w1.d + 2 * HID + 1, 2 * HID + 2, HID, HP, 0, -1, es))) return rc;
     if ((rc = pad_vec(h, L.wvp, L.wv.d, 1, HID, HP))) return rc;
-    if ((rc = pad_vec(h, L.bias_pq, L.b1.d, 1, HID, HP, HP, 2 * HP))) return rc;  // [0 | b1]
+    if ((rc = pad_vec(h, L.bias_pq, L.b1.d, 1, HID, HP, HP, 2 * HP, es))) return rc;  // [0 | b1]
     CK(cudaMemcpy(L.h_wc, L.wc.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(L.h_wd, L.wd.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(L.h_wv, L.wvp.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
@@ -299,7 +302,7 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       PackArgs a{};
       a.src = L.w1.d; a.ld = 2 * HID + 2; a.n_real = HID; a.n_src_off = 0; a.bn = HP; a.n_kc = kc;
       a.seg_len = HP; a.kreal0 = HID; a.kofs0 = half * HID; a.kreal1 = 0; a.kofs1 = 0;
-      a.bias = nullptr; a.bias_k = -1;
+      a.bias = nullptr; a.bias_k = -1; a.scale = es;
       a.dst = L.w1ab_op.as<uint8_t>() + (size_t)half * kc * blk448;
       CK(launch_pack(mode, a, 1, 0));
       h->launches++;
@@ -308,7 +311,7 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       CK(L.w2_op.ensure(kc * blk448));
       PackArgs a{};
       a.src = L.w2.d; a.ld = HID; a.n_real = HID; a.bn = HP; a.n_kc = kc; a.seg_len = HP; a.kreal0 = HID;
-      a.bias = L.b2.d; a.bias_k = BIAS_COL; a.dst = L.w2_op.as<uint8_t>();
+      a.bias = L.b2.d; a.bias_k = BIAS_COL; a.dst = L.w2_op.as<uint8_t>(); a.scale = es;
       CK(launch_pack(mode, a, 1, 0));
       h->launches++;
     }
@@ -477,7 +480,7 @@ static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, f
   a.tiles = h->d_tiles.as<int4>();
   a.n_tiles = h->n_etiles;
   a.node_off = h->d_node_off.as<int>();
-  a.pq = h->pq.as<float>();
+  a.pq = h->pq.p;
   a.x_cur = x_cur;
   a.x0 = h->x0.as<float>();
   a.x_next = x_next;
@@ -501,7 +504,9 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
     a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
     a.w = L.w1ab_op.as<uint8_t>(); a.bias = L.bias_pq.as<float>(); a.m_rows = h->M;
     a.out_f32 = h->pq.as<float>(); a.ldo = 2 * HP; a.n_valid = 2 * HP; a.rowscale = nullptr; a.relu = 0;
-    return launch_gemm_mode<HP, EPI_F32>(mode, a, h->n_mtiles, 2, st);
+    // bf16 mode keeps the P/Q projections in bf16 (halves their HBM and shared-memory traffic; no accuracy cost)
+    if (mode == PREC_BF16) return launch_gemm<PREC_BF16, HP, EPI_BF16>(a, h->n_mtiles, 2, st);
+    return launch_gemm<PREC_TF32, HP, EPI_F32>(a, h->n_mtiles, 2, st);
   };
   float* xa = h->xa.as<float>();
   float* xb = h->xb.as<float>();

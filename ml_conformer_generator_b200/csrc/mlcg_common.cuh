@@ -52,6 +52,18 @@ __device__ __forceinline__ float silu(float x) {
     return __fdividef(x, 1.0f + __expf(-x));
   }
 }
+// SiLU when the argument has already been halved (bf16 fast mode folds the 1/2 into the packed weights, exactly):
+// silu(2h) = h + h*tanh(h).  In precise mode the argument is not scaled and the exact-ish form is used.
+template <bool kFast>
+__device__ __forceinline__ float silu_scaled(float h) {
+  if constexpr (kFast) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  } else {
+    return __fdividef(h, 1.0f + __expf(-h));
+  }
+}
 __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // full-precision SiLU for the fp32 SIMT path
 __device__ __forceinline__ float silu_ref(float x) { return x / (1.0f + expf(-x)); }

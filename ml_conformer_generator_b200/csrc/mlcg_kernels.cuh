@@ -312,6 +312,7 @@ struct PackArgs {
   int seg_len; int kreal0; int kofs0; int kreal1; int kofs1;
   const float* bias; int bias_k;
   uint8_t* dst;
+  float scale;  // multiplies every packed value (0.5 folds SiLU's half-argument into the weights; 0 is treated as 1)
 };
 template <int kMode>
 __global__ void k_pack_weight(const PackArgs a) {
@@ -333,7 +334,7 @@ __global__ void k_pack_weight(const PackArgs a) {
         if (seg < 2 && kk < kreal) x = a.src[(size_t)(a.n_src_off + n) * a.ld + kofs + kk];
         if (a.bias != nullptr && k == a.bias_k) x = a.bias[a.n_src_off + n];
       }
-      v[e] = x;
+      v[e] = x * (a.scale != 0.f ? a.scale : 1.0f);
     }
     uint4 w;
     if constexpr (kMode == PREC_BF16) {
@@ -347,9 +348,10 @@ __global__ void k_pack_weight(const PackArgs a) {
 }
 
 // copy a strided column / vector into a zero-padded fp32 vector of length n_pad
-__global__ void k_pad_vector(const float* __restrict__ src, int stride, int n_real, float* __restrict__ dst, int n_pad) {
+__global__ void k_pad_vector(const float* __restrict__ src, int stride, int n_real, float* __restrict__ dst, int n_pad,
+                             float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) dst[i] = (i < n_real) ? src[(size_t)i * stride] : 0.f;
+  if (i < n_pad) dst[i] = (i < n_real) ? src[(size_t)i * stride] * scale : 0.f;
 }
 
 // fp32 row-major [rows][ld] -> operand format (used by the AdjMatSeer L-multiply output and tests)

@@ -18,7 +18,7 @@ namespace mlcg {
 // ---------------------------------------------------------------------------------------------------------------
 // generic GEMM
 // ---------------------------------------------------------------------------------------------------------------
-enum GemmEpi { EPI_F32 = 0, EPI_SILU_OP = 1, EPI_RESID_OP = 2 };
+enum GemmEpi { EPI_F32 = 0, EPI_SILU_OP = 1, EPI_RESID_OP = 2, EPI_BF16 = 3 };
 
 struct GemmArgs {
   const uint8_t* a0;      // operand-format A, source 0
@@ -30,7 +30,7 @@ struct GemmArgs {
   const uint8_t* w;       // packed weights [n_tile][n_kc][BN x 128 B]
   const float* bias;      // [n_tiles*BN]
   int m_rows;             // valid rows
-  float* out_f32;         // EPI_F32: row-major output
+  float* out_f32;         // EPI_F32: row-major fp32 output; EPI_BF16: the same pointer holds bf16 rows of ldo elements
   int ldo;
   int n_valid;            // EPI_F32: number of valid output columns
   const float* rowscale;  // EPI_F32: optional per-row multiplier of the bias (AdjMatSeer: rowsum of L)
@@ -157,6 +157,18 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
               if (gcol + e + 2 < p.n_valid) orow[e + 2] = o.z;
             }
           }
+        } else if constexpr (kEpi == EPI_BF16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out_f32) + (size_t)grow * p.ldo + gcol;
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            const float4 b0 = __ldg(b4 + (e >> 2)), b1 = __ldg(b4 + (e >> 2) + 1);
+            uint4 o;
+            o.x = pack_bf16x2(v[e + 0] + b0.x, v[e + 1] + b0.y);
+            o.y = pack_bf16x2(v[e + 2] + b0.z, v[e + 3] + b0.w);
+            o.z = pack_bf16x2(v[e + 4] + b1.x, v[e + 5] + b1.y);
+            o.w = pack_bf16x2(v[e + 6] + b1.z, v[e + 7] + b1.w);
+            *reinterpret_cast<uint4*>(orow + e) = o;
+          }
         } else if constexpr (kEpi == EPI_SILU_OP) {
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
@@ -210,19 +222,28 @@ constexpr int EDGE_MAXG = 12;          // max target nodes (groups) per 128-row 
 constexpr int EDGE_MAXN = 39;          // max atoms per molecule (reference config.py MAX_N_NODES)
 constexpr int EDGE_WSLOT = 224 * CHUNK_BYTES;  // 28,672 B: one (K chunk, N half) block of W2
 constexpr int EDGE_NW = 3;             // W ring slots
+constexpr int EDGE_NWMAX = EDGE_NW;
 constexpr int EDGE_NA = 2;             // A ring stages (TMEM columns 448..479 and 480..511)
 constexpr int EDGE_ACOL = 448;         // first TMEM column of the A ring
 constexpr int EDGE_QPITCH = 452;       // floats; 1808 B rows -> conflict-free LDS.128 across consecutive j
 constexpr int EDGE_CT = 512;           // compute threads (16 warps)
 constexpr int EDGE_THREADS = 64 + EDGE_CT;  // warp 0 producer, warp 1 MMA, warps 2..17 compute
 
-struct EdgeSmem {
+// Shared-memory layout.  bf16 mode stores the P/Q projections as bf16 (no accuracy cost: emulated and measured) which
+// halves the A-generation loads and leaves room for a second segment-sum staging buffer.
+template <int kMode>
+struct EdgeSmemT {
+  static constexpr bool BF = (kMode == PREC_BF16);
+  static constexpr int PQ_ESIZE = BF ? 2 : 4;                       // bytes per P/Q element
+  static constexpr int PQ_PITCH = BF ? 912 : EDGE_QPITCH * 4;       // row pitch in bytes (== 16 mod 128: conflict-free)
+  static constexpr int PQ_ROW = HP * PQ_ESIZE;                      // bytes copied per row
+  static constexpr int NSCR = BF ? 2 : 1;                           // 32 KB staging buffers
   static constexpr int W_OFF = 0;
-  static constexpr int SCR_OFF = W_OFF + EDGE_NW * EDGE_WSLOT;   // 32 KB epilogue staging for the segment sum
-  static constexpr int SEL_OFF = SCR_OFF + 2 * A_CHUNK_BYTES;   // 4 KB group selector S[16 x 128] (bf16, K-major SW128)
+  static constexpr int SCR_OFF = W_OFF + EDGE_NW * EDGE_WSLOT;
+  static constexpr int SEL_OFF = SCR_OFF + NSCR * 2 * A_CHUNK_BYTES;   // 4 KB group selector S[16 x 128] (bf16)
   static constexpr int Q_OFF = SEL_OFF + 4096;
-  static constexpr int P_OFF = Q_OFF + ((EDGE_MAXN * EDGE_QPITCH * 4 + 127) / 128) * 128;
-  static constexpr int DOT_OFF = P_OFF + EDGE_MAXG * EDGE_QPITCH * 4;  // [4][128] partial dots
+  static constexpr int P_OFF = Q_OFF + ((EDGE_MAXN * PQ_PITCH + 127) / 128) * 128;
+  static constexpr int DOT_OFF = P_OFF + ((EDGE_MAXG * PQ_PITCH + 127) / 128) * 128;  // [4][128] partial dots
   static constexpr int TRS_OFF = DOT_OFF + 4 * TILE_M * 4;      // [128][3] coordinate messages
   static constexpr int RID_OFF = TRS_OFF + TILE_M * 3 * 4;      // [128] float2 (d2, d0^2)
   static constexpr int RIG_OFF = RID_OFF + TILE_M * 8;          // [128] int  g | j<<8 | valid<<16
@@ -236,7 +257,7 @@ struct EdgeArgs {
   const int4* tiles;   // {molecule, first target node i0, groups ng, atoms N}
   int n_tiles;
   const int* node_off; // [B+1] prefix sum of atom counts
-  const float* pq;     // [nodes][896]: P = W1a.h at 0..447, Q = W1b.h + b1 at 448..895
+  const void* pq;      // [nodes][896] (fp32, or bf16 in bf16 mode): P = W1a.h at 0..447, Q = W1b.h + b1 at 448..895
   const float* x_cur;  // [nodes][3] coordinates at block start
   const float* x0;     // [nodes][3] coordinates at EGNN input
   float* x_next;       // equivariant update output
@@ -246,9 +267,9 @@ struct EdgeArgs {
   uint8_t* agg_op;     // GCL: neighbour aggregate, operand format
   int agg_chunks;
   long long* prof;     // optional [grid][16] per-CTA phase cycle counters (diagnostics), or nullptr
-  float wc[HP];        // first-layer column for d2 (W1[:,840]), zero padded          } constant bank
-  float wd[HP];        // first-layer column for d0^2 (W1[:,841])                      }
-  float wv[HP];        // attention vector (GCL) or coordinate head (equivariant)      }
+  alignas(16) float wc[HP];  // first-layer column for d2 (W1[:,840]), zero padded     } constant bank
+  alignas(16) float wd[HP];  // first-layer column for d0^2 (W1[:,841])                 }
+  alignas(16) float wv[HP];  // attention vector (GCL) or coordinate head (equivariant) }
 };
 
 template <int kMode>
@@ -279,11 +300,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   constexpr int EPC = epc(kMode);
   constexpr int ELEMS = EPC / 4;  // K elements per thread per chunk (16 bf16 / 8 tf32) = 8 TMEM columns
   constexpr bool kSegMma = (kMode == PREC_BF16) && !kEquiv;  // neighbour sum on the tensor core (bf16 mode)
+  using EdgeSmem = EdgeSmemT<kMode>;
+  constexpr bool kPqBf16 = EdgeSmem::BF;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  float* Qs = reinterpret_cast<float*>(gbase + EdgeSmem::Q_OFF);
-  float* Ps = reinterpret_cast<float*>(gbase + EdgeSmem::P_OFF);
+  const uint8_t* Qs = gbase + EdgeSmem::Q_OFF;
+  const uint8_t* Ps = gbase + EdgeSmem::P_OFF;
   float* dots = reinterpret_cast<float*>(gbase + EdgeSmem::DOT_OFF);
   float* trs = reinterpret_cast<float*>(gbase + EdgeSmem::TRS_OFF);
   float2* ri_d = reinterpret_cast<float2*>(gbase + EdgeSmem::RID_OFF);
@@ -291,23 +314,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   uint8_t* scratch = gbase + EdgeSmem::SCR_OFF;
   const uint32_t bar0 = base + EdgeSmem::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
-  auto w_empty = [&](int s) { return bar0 + 8u * (EDGE_NW + s); };
-  auto a_full = [&](int s) { return bar0 + 8u * (2 * EDGE_NW + s); };
-  auto a_empty = [&](int s) { return bar0 + 8u * (2 * EDGE_NW + EDGE_NA + s); };
-  const uint32_t pq_full = bar0 + 8u * (2 * EDGE_NW + 2 * EDGE_NA);
+  auto w_empty = [&](int s) { return bar0 + 8u * (EDGE_NWMAX + s); };
+  auto a_full = [&](int s) { return bar0 + 8u * (2 * EDGE_NWMAX + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * EDGE_NWMAX + EDGE_NA + s); };
+  const uint32_t pq_full = bar0 + 8u * (2 * EDGE_NWMAX + 2 * EDGE_NA);
   const uint32_t pq_empty = pq_full + 8u;
   const uint32_t d_full = pq_full + 16u;
   const uint32_t d_empty = pq_full + 24u;
-  const uint32_t e_full = pq_full + 32u;   // gated messages of one 128-channel block staged (compute -> MMA)
-  const uint32_t e_done = pq_full + 40u;   // segment-sum MMA of that block complete (MMA -> compute)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NW + 2 * EDGE_NA + 6));
+  auto e_full = [&](int b) { return pq_full + 32u + 8u * b; };  // gated messages of a 128-channel block staged
+  auto e_done = [&](int b) { return pq_full + 48u + 8u * b; };  // segment-sum MMA of that block complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NWMAX + 2 * EDGE_NA + 10));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
   const int t_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < EDGE_NW; ++s) {
+    for (int s = 0; s < EDGE_NWMAX; ++s) {
       mbar_init(w_full(s), 1);
       mbar_init(w_empty(s), 1);
     }
@@ -319,8 +342,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     mbar_init(pq_empty, EDGE_CT / 32);
     mbar_init(d_full, 1);
     mbar_init(d_empty, EDGE_CT / 32);
-    mbar_init(e_full, EDGE_CT / 32);
-    mbar_init(e_done, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(e_full(b), EDGE_CT / 32);
+      mbar_init(e_done(b), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
@@ -340,13 +365,15 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         const int node0 = p.node_off[mol];
         mbar_wait(pq_empty, (uint32_t)((it & 1) ^ 1));
         const bool newmol = (mol != prev_mol);
-        mbar_arrive_expect_tx(pq_full, (uint32_t)((ng + (newmol ? n : 0)) * HP * 4));
+        mbar_arrive_expect_tx(pq_full, (uint32_t)((ng + (newmol ? n : 0)) * EdgeSmem::PQ_ROW));
+        const uint8_t* pqb = reinterpret_cast<const uint8_t*>(p.pq);
         for (int g = 0; g < ng; ++g)
-          bulk_g2s(base + EdgeSmem::P_OFF + g * EDGE_QPITCH * 4, p.pq + (size_t)(node0 + i0 + g) * (2 * HP), HP * 4, pq_full);
+          bulk_g2s(base + EdgeSmem::P_OFF + g * EdgeSmem::PQ_PITCH, pqb + (size_t)(node0 + i0 + g) * (2 * EdgeSmem::PQ_ROW),
+                   EdgeSmem::PQ_ROW, pq_full);
         if (newmol)
           for (int j = 0; j < n; ++j)
-            bulk_g2s(base + EdgeSmem::Q_OFF + j * EDGE_QPITCH * 4, p.pq + (size_t)(node0 + j) * (2 * HP) + HP, HP * 4,
-                     pq_full);
+            bulk_g2s(base + EdgeSmem::Q_OFF + j * EdgeSmem::PQ_PITCH,
+                     pqb + (size_t)(node0 + j) * (2 * EdgeSmem::PQ_ROW) + EdgeSmem::PQ_ROW, EdgeSmem::PQ_ROW, pq_full);
         prev_mol = mol;
         for (int kc = 0; kc < p.n_kc; ++kc) {
           for (int nh = 0; nh < 2; ++nh, ++wi) {
@@ -390,15 +417,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // block; E (gated messages, bf16) is staged row-major = MN-major A operand, S is the 0/1 group selector.
           constexpr uint32_t idesc2 = umma_idesc(1, TILE_M, 16) | (1u << 15);  // A is MN-major
           for (int cb = 0; cb < 4; ++cb) {
-            mbar_wait(e_full, (uint32_t)((it * 4 + cb) & 1));
+            const int eb = cb & 1;
+            mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t adesc = umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + ks * 2048, A_CHUNK_BYTES);
+              const uint64_t adesc =
+                  umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + eb * 2 * A_CHUNK_BYTES + ks * 2048, A_CHUNK_BYTES);
               const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (ks >> 2) * 2048) + 2 * (ks & 3);
-              umma<PREC_BF16>(tmem_base + EDGE_ACOL + (cb & 1) * 16, adesc, bdesc, idesc2, ks != 0);
+              umma<PREC_BF16>(tmem_base + EDGE_ACOL + eb * 16, adesc, bdesc, idesc2, ks != 0);
             }
-            umma_commit(e_done);
+            umma_commit(e_done(eb));
           }
         }
       }
@@ -466,8 +495,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       const int info = ri_gj[r];
       const bool valid = (info & 0x10000) != 0;
       const float2 rd = ri_d[r];
-      const float* Prow = Ps + (info & 0xff) * EDGE_QPITCH + qq * ELEMS;         // invalid rows read row 0 (finite)
-      const float* Qrow = Qs + ((info >> 8) & 0xff) * EDGE_QPITCH + qq * ELEMS;
+      const uint8_t* Prow = Ps + (info & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;  // invalid rows read row 0
+      const uint8_t* Qrow = Qs + ((info >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
       mbar_wait(pq_full, (uint32_t)(it & 1));
       if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
@@ -477,14 +506,41 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         const int as = ai % EDGE_NA;
         const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
         float a[ELEMS];
+        float wcv[ELEMS], wdv[ELEMS];  // 128-bit constant-bank loads (k0 is a multiple of 8)
 #pragma unroll
         for (int e = 0; e < ELEMS; e += 4) {
-          const float4 pv = *reinterpret_cast<const float4*>(Prow + kc * EPC + e);
-          const float4 qv = *reinterpret_cast<const float4*>(Qrow + kc * EPC + e);
-          a[e + 0] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 0], fmaf(rd.x, p.wc[k0 + e + 0], pv.x + qv.x)));
-          a[e + 1] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 1], fmaf(rd.x, p.wc[k0 + e + 1], pv.y + qv.y)));
-          a[e + 2] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 2], fmaf(rd.x, p.wc[k0 + e + 2], pv.z + qv.z)));
-          a[e + 3] = silu<kFast>(fmaf(rd.y, p.wd[k0 + e + 3], fmaf(rd.x, p.wc[k0 + e + 3], pv.w + qv.w)));
+          const float4 c4 = *reinterpret_cast<const float4*>(&p.wc[k0 + e]);
+          const float4 d4 = *reinterpret_cast<const float4*>(&p.wd[k0 + e]);
+          wcv[e] = c4.x; wcv[e + 1] = c4.y; wcv[e + 2] = c4.z; wcv[e + 3] = c4.w;
+          wdv[e] = d4.x; wdv[e + 1] = d4.y; wdv[e + 2] = d4.z; wdv[e + 3] = d4.w;
+        }
+        if constexpr (kPqBf16) {
+#pragma unroll
+          for (int e = 0; e < ELEMS; e += 8) {
+            const uint4 pw = *reinterpret_cast<const uint4*>(Prow + (kc * EPC + e) * 2);
+            const uint4 qw = *reinterpret_cast<const uint4*>(Qrow + (kc * EPC + e) * 2);
+            const uint32_t pa[4] = {pw.x, pw.y, pw.z, pw.w}, qa[4] = {qw.x, qw.y, qw.z, qw.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t sum;  // P + Q as packed bf16x2 (one HADD2), then widened to fp32 for the distance terms
+              asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(sum) : "r"(pa[i]), "r"(qa[i]));
+              const float s_lo = __uint_as_float(sum << 16);
+              const float s_hi = __uint_as_float(sum & 0xffff0000u);
+              const int k = e + 2 * i;
+              a[k] = silu_scaled<kFast>(fmaf(rd.y, wdv[k], fmaf(rd.x, wcv[k], s_lo)));
+              a[k + 1] = silu_scaled<kFast>(fmaf(rd.y, wdv[k + 1], fmaf(rd.x, wcv[k + 1], s_hi)));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < ELEMS; e += 4) {
+            const float4 pv = *reinterpret_cast<const float4*>(Prow + (kc * EPC + e) * 4);
+            const float4 qv = *reinterpret_cast<const float4*>(Qrow + (kc * EPC + e) * 4);
+            a[e + 0] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 0], fmaf(rd.x, wcv[e + 0], pv.x + qv.x)));
+            a[e + 1] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 1], fmaf(rd.x, wcv[e + 1], pv.y + qv.y)));
+            a[e + 2] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 2], fmaf(rd.x, wcv[e + 2], pv.z + qv.z)));
+            a[e + 3] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 3], fmaf(rd.x, wcv[e + 3], pv.w + qv.w)));
+          }
         }
         // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416, both modes)
         if (k0 == BIAS_COL - 4) a[4] = 1.0f;
@@ -521,10 +577,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 16; e += 4) {
-          v[e + 0] = silu<kFast>(v[e + 0]); v[e + 1] = silu<kFast>(v[e + 1]);
-          v[e + 2] = silu<kFast>(v[e + 2]); v[e + 3] = silu<kFast>(v[e + 3]);
-          dotp[0] = fmaf(v[e + 0], p.wv[col0 + e + 0], dotp[0]); dotp[1] = fmaf(v[e + 1], p.wv[col0 + e + 1], dotp[1]);
-          dotp[2] = fmaf(v[e + 2], p.wv[col0 + e + 2], dotp[2]); dotp[3] = fmaf(v[e + 3], p.wv[col0 + e + 3], dotp[3]);
+          const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
+          v[e + 0] = silu_scaled<kFast>(v[e + 0]); v[e + 1] = silu_scaled<kFast>(v[e + 1]);
+          v[e + 2] = silu_scaled<kFast>(v[e + 2]); v[e + 3] = silu_scaled<kFast>(v[e + 3]);
+          dotp[0] = fmaf(v[e + 0], w4.x, dotp[0]); dotp[1] = fmaf(v[e + 1], w4.y, dotp[1]);
+          dotp[2] = fmaf(v[e + 2], w4.z, dotp[2]); dotp[3] = fmaf(v[e + 3], w4.w, dotp[3]);
         }
         if constexpr (!kEquiv) tmem_st16(trow + col0, v);
       }
@@ -595,38 +652,44 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           long long s0 = profiling ? clock64() : 0;
           load_gate_pack(0);
           if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }
+          // Round cb stages block cb into staging buffer cb&1 and its MMA writes D2 buffer cb&1; before reusing either,
+          // wait for the MMA of round cb-2 and read its result out.
 #pragma unroll 1
           for (int cb = 0; cb < 4; ++cb) {
-            if (cb > 0) {
-              mbar_wait(e_done, (uint32_t)((it * 4 + cb - 1) & 1));  // staging buffer free, D2(cb-1) ready
+            const int eb = cb & 1;
+            if (cb >= 2) {
+              mbar_wait(e_done(eb), (uint32_t)((it * 2 + ((cb - 2) >> 1)) & 1));
               tc_fence_after();
+              if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }  // wait for the segment-sum MMA
+              readout(cb - 2);
+              if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }  // D2 readout + stores
             }
-            if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }  // wait for the segment-sum MMA
             if (cb * 128 + qq * 32 < HP) {
-              uint8_t* dst = scratch + (qq >> 1) * A_CHUNK_BYTES;
+              uint8_t* dst = scratch + eb * 2 * A_CHUNK_BYTES + (qq >> 1) * A_CHUNK_BYTES;
 #pragma unroll
               for (int pi = 0; pi < 4; ++pi)
                 *reinterpret_cast<uint4*>(dst + sw128_offset(r, (qq & 1) * 4 + pi)) =
                     make_uint4(ew[4 * pi], ew[4 * pi + 1], ew[4 * pi + 2], ew[4 * pi + 3]);
             }
             fence_proxy_async();
-            if (cb == 3) tc_fence_before();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              mbar_arrive(e_full);
+              mbar_arrive(e_full(eb));
               if (cb == 3) mbar_arrive(d_empty);  // all reads of D for this tile are complete
             }
             if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // stage + fence + arrive
             if (cb < 3) load_gate_pack(cb + 1);
             if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }   // TMEM load + gate + pack
-            if (cb > 0) readout(cb - 1);
-            if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }  // D2 readout + stores
           }
-          mbar_wait(e_done, (uint32_t)((it * 4 + 3) & 1));
-          tc_fence_after();
-          if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
-          readout(3);
-          if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
+#pragma unroll 1
+          for (int cb = 2; cb < 4; ++cb) {
+            mbar_wait(e_done(cb & 1), (uint32_t)((it * 2 + (cb >> 1)) & 1));
+            tc_fence_after();
+            if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
+            readout(cb);
+            if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
+          }
         } else {
 #pragma unroll 1
         for (int ch = 0; ch < 7; ++ch) {
@@ -672,7 +735,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       if (profiling) { long long c = clock64(); pacc[4] += c - c0; pacc[6] += 1; }  // pass 2 / coordinate update
     }
     if (profiling)
-      for (int k = 0; k < 16; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = pacc[k];
+      for (int k = 0; k < 11; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = pacc[k];
   }
   tc_fence_before();
   __syncthreads();
