@@ -505,7 +505,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
         const int as = ai % EDGE_NA;
         const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
-        float a[ELEMS];
         float wcv[ELEMS], wdv[ELEMS];  // 128-bit constant-bank loads (k0 is a multiple of 8)
 #pragma unroll
         for (int e = 0; e < ELEMS; e += 4) {
@@ -514,7 +513,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           wcv[e] = c4.x; wcv[e + 1] = c4.y; wcv[e + 2] = c4.z; wcv[e + 3] = c4.w;
           wdv[e] = d4.x; wdv[e + 1] = d4.y; wdv[e + 2] = d4.z; wdv[e + 3] = d4.w;
         }
+        uint32_t w[8];
         if constexpr (kPqBf16) {
+          // bf16 fast mode: everything after the fp32 distance terms is packed bf16x2 -- P+Q (HADD2), tanh (one MUFU
+          // per pair) and h + h*tanh(h) (HFMA2); the result is directly the packed A-operand word.
 #pragma unroll
           for (int e = 0; e < ELEMS; e += 8) {
             const uint4 pw = *reinterpret_cast<const uint4*>(Prow + (kc * EPC + e) * 2);
@@ -522,16 +524,21 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             const uint32_t pa[4] = {pw.x, pw.y, pw.z, pw.w}, qa[4] = {qw.x, qw.y, qw.z, qw.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint32_t sum;  // P + Q as packed bf16x2 (one HADD2), then widened to fp32 for the distance terms
+              uint32_t sum, h2, t2, a2;
               asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(sum) : "r"(pa[i]), "r"(qa[i]));
-              const float s_lo = __uint_as_float(sum << 16);
-              const float s_hi = __uint_as_float(sum & 0xffff0000u);
               const int k = e + 2 * i;
-              a[k] = silu_scaled<kFast>(fmaf(rd.y, wdv[k], fmaf(rd.x, wcv[k], s_lo)));
-              a[k + 1] = silu_scaled<kFast>(fmaf(rd.y, wdv[k + 1], fmaf(rd.x, wcv[k + 1], s_hi)));
+              const float h_lo = fmaf(rd.y, wdv[k], fmaf(rd.x, wcv[k], __uint_as_float(sum << 16)));
+              const float h_hi = fmaf(rd.y, wdv[k + 1], fmaf(rd.x, wcv[k + 1], __uint_as_float(sum & 0xffff0000u)));
+              h2 = pack_bf16x2(h_lo, h_hi);
+              asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
+              asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a2) : "r"(h2), "r"(t2));
+              w[(e >> 1) + i] = a2;
             }
           }
+          // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416): low half of word 2
+          if (k0 == BIAS_COL - 4) w[2] = (w[2] & 0xffff0000u) | 0x3f80u;
         } else {
+          float a[ELEMS];
 #pragma unroll
           for (int e = 0; e < ELEMS; e += 4) {
             const float4 pv = *reinterpret_cast<const float4*>(Prow + (kc * EPC + e) * 4);
@@ -541,14 +548,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             a[e + 2] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 2], fmaf(rd.x, wcv[e + 2], pv.z + qv.z)));
             a[e + 3] = silu_scaled<kFast>(fmaf(rd.y, wdv[e + 3], fmaf(rd.x, wcv[e + 3], pv.w + qv.w)));
           }
-        }
-        // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416, both modes)
-        if (k0 == BIAS_COL - 4) a[4] = 1.0f;
-        uint32_t w[8];
+          if (k0 == BIAS_COL - 4) a[4] = 1.0f;  // constant-1 column carrying b2
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if constexpr (kMode == PREC_BF16) w[i] = pack_bf16x2(a[2 * i], a[2 * i + 1]);
-          else w[i] = f32_to_tf32(a[i]);
+          for (int i = 0; i < 8; ++i) w[i] = f32_to_tf32(a[i]);
         }
         long long cw0 = profiling ? clock64() : 0;
         mbar_wait(a_empty(as), ((ai / EDGE_NA) & 1) ^ 1u);
@@ -569,7 +571,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       tc_fence_after();
       if (profiling) { long long c = clock64(); pacc[2] += c - c0; c0 = c; }  // MMA tail
       float dotp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
+      // thread (row r, quarter qq) owns output columns 112*qq .. 112*qq+111 in 7 runs of 16.  GCL bf16 mode keeps the
+      // SiLU'd messages as packed bf16 in registers (ew) for pass 2; the other variants write them back to TMEM.
+      uint32_t ew[kSegMma ? 56 : 1];
+#pragma unroll
       for (int ch = 0; ch < 7; ++ch) {
         const int col0 = qq * 112 + ch * 16;  // warp-uniform
         float v[16];
@@ -583,10 +588,20 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           dotp[0] = fmaf(v[e + 0], w4.x, dotp[0]); dotp[1] = fmaf(v[e + 1], w4.y, dotp[1]);
           dotp[2] = fmaf(v[e + 2], w4.z, dotp[2]); dotp[3] = fmaf(v[e + 3], w4.w, dotp[3]);
         }
-        if constexpr (!kEquiv) tmem_st16(trow + col0, v);
+        if constexpr (kSegMma) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ew[ch * 8 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        } else if constexpr (!kEquiv) {
+          tmem_st16(trow + col0, v);
+        }
+      }
+      if constexpr (kSegMma) {  // D has been fully consumed: the next tile's MMAs may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
       }
       dots[qq * TILE_M + r] = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
-      if constexpr (!kEquiv) tmem_wait_st();
+      if constexpr (!kEquiv && !kSegMma) tmem_wait_st();
       named_bar_sync(1, EDGE_CT);
       if (profiling) { long long c = clock64(); pacc[3] += c - c0; c0 = c; }  // pass 1
       const float full_dot = (dots[r] + dots[TILE_M + r]) + (dots[2 * TILE_M + r] + dots[3 * TILE_M + r]);
@@ -612,26 +627,22 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         // e_ij = m_ij * sigmoid(w_a.m_ij + b_a); agg_i = sum_j e_ij / 100   (reference egnn.py:48-51, 59-64)
         const float gate = valid ? sigmoid_acc(full_dot + p.att_bias) : 0.f;
         if constexpr (kSegMma) {
-          // thread (row r, qq) stages channels cb*128 + qq*32 .. +31 of each 128-channel block cb as bf16
-          uint32_t ew[16];
-          auto load_gate_pack = [&](int cb) {
-            if (cb * 128 + qq * 32 < HP) {
-              float v[32];
-              tmem_ld32(trow + cb * 128 + qq * 32, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ew[i] = pack_bf16x2(v[2 * i] * gate, v[2 * i + 1] * gate);
-            }
-          };
-          // D2 readout: lane = channel cb*128 + r, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
-          const int rd_piece = (r >> 3) & 7;  // 16-byte piece of this thread's channel inside its 64-channel chunk
+          // Staging blocks: block cb < 3 = runs 2cb, 2cb+1 of every quarter (32 channels x 4 quarters = 128 MMA rows,
+          // row m = 32*qq + c); block 3 = run 6 of every quarter (16 channels x 4 = 64 rows, m = 16*qq + c).
+          uint32_t g2;
+          {
+            const uint32_t gb = pack_bf16x2(gate, gate);
+            g2 = gb;
+          }
+          // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
           auto readout = [&](int cb) {
             float v[16];
             tmem_ld16(trow + EDGE_ACOL + (cb & 1) * 16, v);
             tmem_wait_ld();
-            const int ch = cb * 128 + r;
-            if (ch < HP) {
+            const int ch = (cb < 3) ? 112 * (r >> 5) + 32 * cb + (r & 31) : 112 * (r >> 4) + 96 + (r & 15);
+            if (cb < 3 || r < 64) {
               uint8_t* cbase = p.agg_op + (size_t)(ch >> 6) * A_CHUNK_BYTES + (ch & 7) * 2;
+              const int rd_piece = (ch >> 3) & 7;
 #pragma unroll
               for (int gi = 0; gi < 3; ++gi) {
                 const int g = qq + 4 * gi;
@@ -650,11 +661,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             tc_fence_before();
           };
           long long s0 = profiling ? clock64() : 0;
-          load_gate_pack(0);
-          if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }
           // Round cb stages block cb into staging buffer cb&1 and its MMA writes D2 buffer cb&1; before reusing either,
           // wait for the MMA of round cb-2 and read its result out.
-#pragma unroll 1
+#pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             const int eb = cb & 1;
             if (cb >= 2) {
@@ -664,23 +673,32 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
               readout(cb - 2);
               if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }  // D2 readout + stores
             }
-            if (cb * 128 + qq * 32 < HP) {
-              uint8_t* dst = scratch + eb * 2 * A_CHUNK_BYTES + (qq >> 1) * A_CHUNK_BYTES;
+            uint8_t* sbuf = scratch + eb * 2 * A_CHUNK_BYTES;
+            if (cb < 3) {
+              uint8_t* dst = sbuf + (qq >> 1) * A_CHUNK_BYTES;
 #pragma unroll
-              for (int pi = 0; pi < 4; ++pi)
-                *reinterpret_cast<uint4*>(dst + sw128_offset(r, (qq & 1) * 4 + pi)) =
-                    make_uint4(ew[4 * pi], ew[4 * pi + 1], ew[4 * pi + 2], ew[4 * pi + 3]);
+              for (int pi = 0; pi < 4; ++pi) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o[i]) : "r"(ew[cb * 16 + pi * 4 + i]), "r"(g2));
+                *reinterpret_cast<uint4*>(dst + sw128_offset(r, (qq & 1) * 4 + pi)) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            } else {
+#pragma unroll
+              for (int pi = 0; pi < 2; ++pi) {
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o[i]) : "r"(ew[48 + pi * 4 + i]), "r"(g2));
+                *reinterpret_cast<uint4*>(sbuf + sw128_offset(r, qq * 2 + pi)) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
             }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-              mbar_arrive(e_full(eb));
-              if (cb == 3) mbar_arrive(d_empty);  // all reads of D for this tile are complete
-            }
-            if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // stage + fence + arrive
-            if (cb < 3) load_gate_pack(cb + 1);
-            if (profiling) { long long c = clock64(); pacc[8] += c - s0; s0 = c; }   // TMEM load + gate + pack
+            if (lane == 0) mbar_arrive(e_full(eb));
+            if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate + stage + fence + arrive
           }
 #pragma unroll 1
           for (int cb = 2; cb < 4; ++cb) {
