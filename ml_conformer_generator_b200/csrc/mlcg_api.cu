@@ -130,21 +130,47 @@ static cudaError_t launch_gemm_mode(int mode, const GemmArgs& a, int n_mtiles, i
   return mode == PREC_BF16 ? launch_gemm<PREC_BF16, BN, kEpi>(a, n_mtiles, n_ntiles, st)
                            : launch_gemm<PREC_TF32, BN, kEpi>(a, n_mtiles, n_ntiles, st);
 }
-template <int kMode, bool kEquiv>
+template <int kMode, bool kEquiv, bool kPair>
 static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv>, cudaFuncAttributeMaxDynamicSharedMemorySize, EdgeSmemT<kMode>::ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         EdgeSmemT<kMode>::ALLOC);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_tc_edge<kMode, kEquiv><<<grid, EDGE_THREADS, EdgeSmemT<kMode>::ALLOC, st>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(EDGE_THREADS);
+  cfg.dynamicSmemBytes = EdgeSmemT<kMode>::ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair>, a);
+}
+// CTA-pair mode (default) needs an even grid; MLCG_EDGE_PAIR=0 selects the single-CTA kernel.
+static bool edge_pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLCG_EDGE_PAIR");
+    v = (e == nullptr) ? 1 : (atoi(e) != 0);
+  }
+  return v != 0;
 }
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
-  if (mode == PREC_BF16) return equiv ? launch_edge<PREC_BF16, true>(a, grid, st) : launch_edge<PREC_BF16, false>(a, grid, st);
-  return equiv ? launch_edge<PREC_TF32, true>(a, grid, st) : launch_edge<PREC_TF32, false>(a, grid, st);
+  const bool pair = edge_pair_mode() && grid >= 2;
+  if (pair) grid &= ~1;
+  if (mode == PREC_BF16) {
+    if (pair) return equiv ? launch_edge<PREC_BF16, true, true>(a, grid, st) : launch_edge<PREC_BF16, false, true>(a, grid, st);
+    return equiv ? launch_edge<PREC_BF16, true, false>(a, grid, st) : launch_edge<PREC_BF16, false, false>(a, grid, st);
+  }
+  if (pair) return equiv ? launch_edge<PREC_TF32, true, true>(a, grid, st) : launch_edge<PREC_TF32, false, true>(a, grid, st);
+  return equiv ? launch_edge<PREC_TF32, true, false>(a, grid, st) : launch_edge<PREC_TF32, false, false>(a, grid, st);
 }
 static cudaError_t launch_pack(int mode, const PackArgs& a, int n_ntiles, cudaStream_t st) {
   dim3 grid(a.n_kc, n_ntiles);

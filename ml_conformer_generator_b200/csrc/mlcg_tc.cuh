@@ -272,6 +272,32 @@ struct EdgeArgs {
   alignas(16) float wv[HP];  // attention vector (GCL) or coordinate head (equivariant) }
 };
 
+// CTA-pair variants (cta_group::2): issued by the leader CTA only; M = 256 spans both CTAs' TMEM, B is split in N
+// between the two CTAs' shared memories.
+template <int kMode>
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kMode == PREC_BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_ss_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int kMode>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   if constexpr (kMode == PREC_BF16) {
@@ -294,7 +320,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
-template <int kMode, bool kEquiv>
+// kPair: the kernel is launched in clusters of 2 CTAs that share the W2 stream (each CTA holds half of every W2 block,
+// tcgen05.mma.cta_group::2 with M = 256 covers both CTAs' tiles): halves the shared-memory traffic of the weight stream,
+// which otherwise saturates the 128 B/clk crossbar on its own (64 B/clk of bulk-copy writes + 64 B/clk of operand reads).
+template <int kMode, bool kEquiv, bool kPair>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_constant__ EdgeArgs p) {
   constexpr bool kFast = (kMode == PREC_BF16);
   constexpr int EPC = epc(kMode);
@@ -323,44 +352,78 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   const uint32_t d_empty = pq_full + 24u;
   auto e_full = [&](int b) { return pq_full + 32u + 8u * b; };  // gated messages of a 128-channel block staged
   auto e_done = [&](int b) { return pq_full + 48u + 8u * b; };  // segment-sum MMA of that block complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NWMAX + 2 * EDGE_NA + 10));
+  auto w_peer = [&](int s) { return pq_full + 64u + 8u * s; };  // pair mode: the peer CTA's half of W slot s has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NWMAX + 2 * EDGE_NA + 8 + EDGE_NW));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
-  const int t_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+  // Tile range.  Single-CTA mode: a contiguous range per CTA.  Pair mode: a contiguous range per pair, first half to
+  // CTA 0 and second half to CTA 1; both CTAs run the same number of iterations (the MMAs are joint), CTA 1 pads with
+  // an empty "ghost" tile when the range is odd.
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
+  int t_begin, t_end, n_iter;
+  if constexpr (kPair) {
+    const int npairs = gridDim.x >> 1, pr = blockIdx.x >> 1;
+    const int T0 = (int)(((long long)pr * p.n_tiles) / npairs), T1 = (int)(((long long)(pr + 1) * p.n_tiles) / npairs);
+    n_iter = (T1 - T0 + 1) >> 1;
+    t_begin = crank == 0 ? T0 : T0 + n_iter;
+    t_end = crank == 0 ? T0 + n_iter : T1;
+  } else {
+    t_begin = (int)(((long long)blockIdx.x * p.n_tiles) / gridDim.x);
+    t_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
+    n_iter = t_end - t_begin;
+  }
+  auto fetch_tile = [&](int it) -> int4 {
+    const int t = t_begin + it;
+    if (t < t_end) return p.tiles[t];
+    int4 g = p.tiles[t_end - 1 >= 0 ? max(t_end - 1, 0) : 0];  // ghost: same molecule, no target atoms
+    g.y = 0;
+    g.z = 0;
+    return g;
+  };
+  constexpr int NARR = kPair ? 2 * (EDGE_CT / 32) : (EDGE_CT / 32);  // arrivals on the barriers the MMA issuer waits on
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < EDGE_NWMAX; ++s) {
       mbar_init(w_full(s), 1);
       mbar_init(w_empty(s), 1);
+      mbar_init(w_peer(s), 1);
     }
     for (int s = 0; s < EDGE_NA; ++s) {
-      mbar_init(a_full(s), EDGE_CT / 32);
+      mbar_init(a_full(s), NARR);
       mbar_init(a_empty(s), 1);
     }
     mbar_init(pq_full, 1);
     mbar_init(pq_empty, EDGE_CT / 32);
     mbar_init(d_full, 1);
-    mbar_init(d_empty, EDGE_CT / 32);
+    mbar_init(d_empty, NARR);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(e_full(b), EDGE_CT / 32);
+      mbar_init(e_full(b), NARR);
       mbar_init(e_done(b), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(smem_u32(tmem_slot));
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair<512>(smem_u32(tmem_slot));
+    else tmem_alloc<512>(smem_u32(tmem_slot));
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // arrive on a barrier the MMA issuer (leader CTA) waits on
+  auto arrive_leader = [&](uint32_t bar) {
+    if constexpr (kPair) mbar_arrive_cluster(mapa(bar, 0));
+    else mbar_arrive(bar);
+  };
 
   if (warp == 0) {
     // ===================== bulk-copy producer =====================
     if (lane == 0) {
       int prev_mol = -1;
       uint32_t wi = 0;
-      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-        const int4 ti = p.tiles[t];
+      for (int it = 0; it < n_iter; ++it) {
+        const int4 ti = fetch_tile(it);
         const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
         const int node0 = p.node_off[mol];
         mbar_wait(pq_empty, (uint32_t)((it & 1) ^ 1));
@@ -375,59 +438,108 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             bulk_g2s(base + EdgeSmem::Q_OFF + j * EdgeSmem::PQ_PITCH,
                      pqb + (size_t)(node0 + j) * (2 * EdgeSmem::PQ_ROW) + EdgeSmem::PQ_ROW, EdgeSmem::PQ_ROW, pq_full);
         prev_mol = mol;
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          for (int nh = 0; nh < 2; ++nh, ++wi) {
+        if constexpr (kPair) {
+          // one ring slot per K chunk: this CTA's 112 rows of each N half (2 x 14,336 B)
+          for (int kc = 0; kc < p.n_kc; ++kc, ++wi) {
             const int s = wi % EDGE_NW;
-            const uint32_t ph = (wi / EDGE_NW) & 1;
-            mbar_wait(w_empty(s), ph ^ 1u);
+            mbar_wait(w_empty(s), ((wi / EDGE_NW) & 1) ^ 1u);
             mbar_arrive_expect_tx(w_full(s), EDGE_WSLOT);
-            bulk_g2s(base + EdgeSmem::W_OFF + s * EDGE_WSLOT, p.w2 + ((size_t)kc * 2 + nh) * EDGE_WSLOT, EDGE_WSLOT,
-                     w_full(s));
+            const uint8_t* src = p.w2 + (size_t)kc * 2 * EDGE_WSLOT + crank * (EDGE_WSLOT / 2);
+            const uint32_t dst = base + EdgeSmem::W_OFF + s * EDGE_WSLOT;
+            bulk_g2s(dst, src, EDGE_WSLOT / 2, w_full(s));
+            bulk_g2s(dst + EDGE_WSLOT / 2, src + EDGE_WSLOT, EDGE_WSLOT / 2, w_full(s));
+          }
+        } else {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            for (int nh = 0; nh < 2; ++nh, ++wi) {
+              const int s = wi % EDGE_NW;
+              const uint32_t ph = (wi / EDGE_NW) & 1;
+              mbar_wait(w_empty(s), ph ^ 1u);
+              mbar_arrive_expect_tx(w_full(s), EDGE_WSLOT);
+              bulk_g2s(base + EdgeSmem::W_OFF + s * EDGE_WSLOT, p.w2 + ((size_t)kc * 2 + nh) * EDGE_WSLOT, EDGE_WSLOT,
+                       w_full(s));
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== tcgen05.mma issuer (A from TMEM, B from shared memory) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, TILE_M, 224);
+    if (lane == 0 && kPair && crank == 1) {
+      // peer CTA: relay "my half of W slot s has landed" to the leader, which issues the joint MMAs
+      uint32_t wi = 0;
+      for (int it = 0; it < n_iter; ++it)
+        for (int kc = 0; kc < p.n_kc; ++kc, ++wi) {
+          const int s = wi % EDGE_NW;
+          mbar_wait(w_full(s), (wi / EDGE_NW) & 1);
+          mbar_arrive_cluster(mapa(w_peer(s), 0));
+        }
+    } else if (lane == 0) {
+      constexpr int MM = kPair ? 2 * TILE_M : TILE_M;
+      constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, MM, 224);
       uint32_t wi = 0, ai = 0;
-      for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
-        mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));
+      for (int it = 0; it < n_iter; ++it) {
+        if constexpr (kPair) mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));
+        else mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));
         tc_fence_after();
         for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
           const int as = ai % EDGE_NA;
-          mbar_wait(a_full(as), (ai / EDGE_NA) & 1);
+          if constexpr (kPair) mbar_wait(a_full(as), (ai / EDGE_NA) & 1);
+          else mbar_wait(a_full(as), (ai / EDGE_NA) & 1);
           const uint32_t a_tmem = tmem_base + EDGE_ACOL + as * 32;
-          for (int nh = 0; nh < 2; ++nh, ++wi) {
+          if constexpr (kPair) {
             const int ws = wi % EDGE_NW;
             mbar_wait(w_full(ws), (wi / EDGE_NW) & 1);
+            mbar_wait(w_peer(ws), (wi / EDGE_NW) & 1);
             tc_fence_after();
-            const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::W_OFF + ws * EDGE_WSLOT);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ts<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
-            umma_commit(w_empty(ws));
+            for (int nh = 0; nh < 2; ++nh) {
+              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::W_OFF + ws * EDGE_WSLOT + nh * (EDGE_WSLOT / 2));
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts_pair<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+            }
+            umma_commit_pair(w_empty(ws), 3);
+            ++wi;
+            umma_commit_pair(a_empty(as), 3);
+          } else {
+            for (int nh = 0; nh < 2; ++nh, ++wi) {
+              const int ws = wi % EDGE_NW;
+              mbar_wait(w_full(ws), (wi / EDGE_NW) & 1);
+              tc_fence_after();
+              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::W_OFF + ws * EDGE_WSLOT);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ts<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+              umma_commit(w_empty(ws));
+            }
+            umma_commit(a_empty(as));
           }
-          umma_commit(a_empty(as));
         }
-        umma_commit(d_full);
+        if constexpr (kPair) umma_commit_pair(d_full, 3);
+        else umma_commit(d_full);
         if constexpr (kSegMma) {
           // segment sum over neighbours on the tensor core: D2[128 channels x 16 groups] = E^T . S^T per 128-channel
           // block; E (gated messages, bf16) is staged row-major = MN-major A operand, S is the 0/1 group selector.
-          constexpr uint32_t idesc2 = umma_idesc(1, TILE_M, 16) | (1u << 15);  // A is MN-major
+          // Pair mode: M = 256 covers both CTAs' messages, N = 32 = [S of CTA 0 ; S of CTA 1]; CTA r uses D2 columns
+          // 16r .. 16r+15.
+          constexpr uint32_t idesc2 = umma_idesc(1, MM, kPair ? 32 : 16) | (1u << 15);  // A is MN-major
+          constexpr int D2W = kPair ? 32 : 16;
           for (int cb = 0; cb < 4; ++cb) {
             const int eb = cb & 1;
-            mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
+            if constexpr (kPair) mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
+            else mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
             tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t adesc =
                   umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + eb * 2 * A_CHUNK_BYTES + ks * 2048, A_CHUNK_BYTES);
               const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (ks >> 2) * 2048) + 2 * (ks & 3);
-              umma<PREC_BF16>(tmem_base + EDGE_ACOL + eb * 16, adesc, bdesc, idesc2, ks != 0);
+              if constexpr (kPair) umma_ss_bf16_pair(tmem_base + EDGE_ACOL + eb * D2W, adesc, bdesc, idesc2, ks != 0);
+              else umma<PREC_BF16>(tmem_base + EDGE_ACOL + eb * D2W, adesc, bdesc, idesc2, ks != 0);
             }
-            umma_commit(e_done(eb));
+            if constexpr (kPair) umma_commit_pair(e_done(eb), 3);
+            else umma_commit(e_done(eb));
           }
         }
       }
@@ -445,9 +557,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     const bool profiling = (p.prof != nullptr) && (ct == 0);
     if (profiling)
       for (int k = 0; k < 16; ++k) pacc[k] = 0;
-    for (int t = t_begin, it = 0; t < t_end; ++t, ++it) {
+    for (int it = 0; it < n_iter; ++it) {
       long long c0 = profiling ? clock64() : 0;
-      const int4 ti = p.tiles[t];
+      const int4 ti = fetch_tile(it);
       const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
       const int nm1 = max(n - 1, 1);
       const int nrows = ng * (n - 1);
@@ -560,7 +672,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(as));  // one arrival per warp
+        if (lane == 0) arrive_leader(a_full(as));  // one arrival per warp
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
@@ -598,7 +710,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       if constexpr (kSegMma) {  // D has been fully consumed: the next tile's MMAs may overwrite it
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty);
+        if (lane == 0) arrive_leader(d_empty);
       }
       dots[qq * TILE_M + r] = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
       if constexpr (!kEquiv && !kSegMma) tmem_wait_st();
@@ -609,7 +721,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         // x_i += sum_j unit_ij * phi_ij / 100   (reference egnn.py:124-134)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d_empty);
+        if (lane == 0) arrive_leader(d_empty);
         if (qq == 0) {
           const float phi = valid ? full_dot : 0.f;
           trs[r * 3 + 0] *= phi; trs[r * 3 + 1] *= phi; trs[r * 3 + 2] *= phi;
@@ -637,7 +749,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
           auto readout = [&](int cb) {
             float v[16];
-            tmem_ld16(trow + EDGE_ACOL + (cb & 1) * 16, v);
+            tmem_ld16(trow + EDGE_ACOL + (cb & 1) * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), v);
             tmem_wait_ld();
             const int ch = (cb < 3) ? 112 * (r >> 5) + 32 * cb + (r & 31) : 112 * (r >> 4) + 96 + (r & 15);
             if (cb < 3 || r < 64) {
@@ -697,7 +809,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(e_full(eb));
+            if (lane == 0) arrive_leader(e_full(eb));
             if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate + stage + fence + arrive
           }
 #pragma unroll 1
@@ -718,7 +830,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           if (ch == 6) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(d_empty);  // last TMEM read of this tile is complete
+            if (lane == 0) arrive_leader(d_empty);  // last TMEM read of this tile is complete
           }
           named_bar_sync(1, EDGE_CT);  // previous chunk's readers are done with the scratch
           // staging: two 16 KB halves of [128 rows x 32 fp32]; quarter qq lands in half qq>>1, columns (qq&1)*16..
@@ -757,7 +869,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if constexpr (kPair) {
+    cluster_sync_all();  // the peer may still be reading this CTA's shared memory / TMEM through the joint MMAs
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+  } else {
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+  }
 }
 
 }  // namespace mlcg
