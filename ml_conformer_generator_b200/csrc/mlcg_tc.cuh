@@ -241,13 +241,13 @@ struct EdgeSmemT {
   static constexpr int W_OFF = 0;
   static constexpr int SCR_OFF = W_OFF + EDGE_NW * EDGE_WSLOT;
   static constexpr int SEL_OFF = SCR_OFF + NSCR * 2 * A_CHUNK_BYTES;   // 4 KB group selector S[16 x 128] (bf16)
-  static constexpr int Q_OFF = SEL_OFF + 4096;
+  static constexpr int Q_OFF = SEL_OFF + 2 * 4096;   // selector is double-buffered (next tile's is built during the MMA tail)
   static constexpr int P_OFF = Q_OFF + ((EDGE_MAXN * PQ_PITCH + 127) / 128) * 128;
   static constexpr int DOT_OFF = P_OFF + ((EDGE_MAXG * PQ_PITCH + 127) / 128) * 128;  // [4][128] partial dots
-  static constexpr int TRS_OFF = DOT_OFF + 4 * TILE_M * 4;      // [128][3] coordinate messages
-  static constexpr int RID_OFF = TRS_OFF + TILE_M * 3 * 4;      // [128] float2 (d2, d0^2)
-  static constexpr int RIG_OFF = RID_OFF + TILE_M * 8;          // [128] int  g | j<<8 | valid<<16
-  static constexpr int PROF_OFF = RIG_OFF + TILE_M * 4;         // 16 x int64 phase counters (diagnostics)
+  static constexpr int TRS_OFF = DOT_OFF + 4 * TILE_M * 4;      // [2][128][3] coordinate messages
+  static constexpr int RID_OFF = TRS_OFF + 2 * TILE_M * 3 * 4;  // [2][128] float2 (d2, d0^2)
+  static constexpr int RIG_OFF = RID_OFF + 2 * TILE_M * 8;      // [2][128] int  g | j<<8 | valid<<16
+  static constexpr int PROF_OFF = RIG_OFF + 2 * TILE_M * 4;         // 16 x int64 phase counters (diagnostics)
   static constexpr int BAR_OFF = PROF_OFF + 128;
   static constexpr int TOTAL = BAR_OFF + 256;
   static constexpr int ALLOC = TOTAL + 1024;
@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   const uint8_t* Qs = gbase + EdgeSmem::Q_OFF;
   const uint8_t* Ps = gbase + EdgeSmem::P_OFF;
   float* dots = reinterpret_cast<float*>(gbase + EdgeSmem::DOT_OFF);
-  float* trs = reinterpret_cast<float*>(gbase + EdgeSmem::TRS_OFF);
-  float2* ri_d = reinterpret_cast<float2*>(gbase + EdgeSmem::RID_OFF);
-  int* ri_gj = reinterpret_cast<int*>(gbase + EdgeSmem::RIG_OFF);
+  float* trs_all = reinterpret_cast<float*>(gbase + EdgeSmem::TRS_OFF);
+  float2* ri_d_all = reinterpret_cast<float2*>(gbase + EdgeSmem::RID_OFF);
+  int* ri_gj_all = reinterpret_cast<int*>(gbase + EdgeSmem::RIG_OFF);
   uint8_t* scratch = gbase + EdgeSmem::SCR_OFF;
   const uint32_t bar0 = base + EdgeSmem::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
@@ -534,9 +534,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             for (int ks = 0; ks < 8; ++ks) {
               const uint64_t adesc =
                   umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + eb * 2 * A_CHUNK_BYTES + ks * 2048, A_CHUNK_BYTES);
-              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (ks >> 2) * 2048) + 2 * (ks & 3);
-              if constexpr (kPair) umma_ss_bf16_pair(tmem_base + EDGE_ACOL + eb * D2W, adesc, bdesc, idesc2, ks != 0);
-              else umma<PREC_BF16>(tmem_base + EDGE_ACOL + eb * D2W, adesc, bdesc, idesc2, ks != 0);
+              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (it & 1) * 4096 + (ks >> 2) * 2048) + 2 * (ks & 3);
+              // results go to D columns cb*D2W.. : D is free (every warp arrived on e_full only after its pass 1) and the
+              // next tile's MMAs cannot start before every warp has finished this tile's readout
+              if constexpr (kPair) umma_ss_bf16_pair(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
+              else umma<PREC_BF16>(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
             }
             if constexpr (kPair) umma_commit_pair(e_done(eb), 3);
             else umma_commit(e_done(eb));
@@ -557,14 +559,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     const bool profiling = (p.prof != nullptr) && (ct == 0);
     if (profiling)
       for (int k = 0; k < 16; ++k) pacc[k] = 0;
-    for (int it = 0; it < n_iter; ++it) {
-      long long c0 = profiling ? clock64() : 0;
-      const int4 ti = fetch_tile(it);
-      const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
+    // Row metadata (d2, d0^2, group / neighbour ids, unit vectors) and the group selector of a tile are double-buffered:
+    // they are computed for tile it+1 while tile it waits for its last MMAs.
+    auto tile_setup = [&](const int4 ti, int buf) {
+      const int i0 = ti.y, ng = ti.z, n = ti.w;
       const int nm1 = max(n - 1, 1);
       const int nrows = ng * (n - 1);
-      const int node0 = p.node_off[mol];
-      // ---- per-row metadata (one thread per row) ----
+      const int node0 = p.node_off[ti.x];
       if (ct < TILE_M) {
         const int rr = ct;
         const bool rvalid = rr < nrows;
@@ -579,17 +580,18 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         const float* yi = p.x0 + (size_t)(node0 + i) * 3;
         const float* yj = p.x0 + (size_t)(node0 + j) * 3;
         const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
-        ri_d[rr] = make_float2(d2, ex * ex + ey * ey + ez * ez);
-        ri_gj[rr] = g | (j << 8) | (rvalid ? 0x10000 : 0);
+        ri_d_all[buf * TILE_M + rr] = make_float2(d2, ex * ex + ey * ey + ez * ez);
+        ri_gj_all[buf * TILE_M + rr] = g | (j << 8) | (rvalid ? 0x10000 : 0);
         if constexpr (kEquiv) {
           const float inv = 1.0f / sqrtf(d2 + 1e-8f);
-          trs[rr * 3 + 0] = dx * inv; trs[rr * 3 + 1] = dy * inv; trs[rr * 3 + 2] = dz * inv;
+          float* tr = trs_all + buf * TILE_M * 3 + rr * 3;
+          tr[0] = dx * inv; tr[1] = dy * inv; tr[2] = dz * inv;
         }
       }
       if constexpr (kSegMma) {
         // S[g][k] = 1 if tile row k belongs to target node g: thread = (group g, 16-byte piece of 8 rows)
-        if (ct < 256) {
-          const int g = ct >> 4, piece = ct & 15;
+        if (ct >= 256) {
+          const int g = (ct - 256) >> 4, piece = ct & 15;
           const int lo_k = g * nm1, hi_k = min(lo_k + n - 1, nrows);  // rows [lo_k, hi_k) belong to group g
           uint32_t w[4];
 #pragma unroll
@@ -599,11 +601,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             const uint32_t hi = (k + 1 >= lo_k && k + 1 < hi_k) ? 0x3f80u : 0u;
             w[e] = lo | (hi << 16);
           }
-          *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
+          *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + buf * 4096 + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
               make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      named_bar_sync(1, EDGE_CT);
+    };
+    if (n_iter > 0) tile_setup(fetch_tile(0), 0);
+    named_bar_sync(1, EDGE_CT);
+    for (int it = 0; it < n_iter; ++it) {
+      long long c0 = profiling ? clock64() : 0;
+      const int4 ti = fetch_tile(it);
+      const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
+      const int nm1 = max(n - 1, 1);
+      const int node0 = p.node_off[mol];
+      const int buf = it & 1;
+      float* trs = trs_all + buf * TILE_M * 3;
+      const float2* ri_d = ri_d_all + buf * TILE_M;
+      const int* ri_gj = ri_gj_all + buf * TILE_M;
       const int info = ri_gj[r];
       const bool valid = (info & 0x10000) != 0;
       const float2 rd = ri_d[r];
@@ -676,6 +690,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
+      if (it + 1 < n_iter) tile_setup(fetch_tile(it + 1), buf ^ 1);  // overlaps this tile's last MMAs
       if (profiling) { long long c = clock64(); pacc[1] += c - c0; c0 = c; }  // A generation (incl. back-pressure)
 
       // ---- epilogue pass 1: m = SiLU(D) (written back to TMEM for GCL), partial dot with the gate / coord vector ----
@@ -692,17 +707,40 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         float v[16];
         tmem_ld16(trow + col0, v);
         tmem_wait_ld();
+        if constexpr (kFast) {
+          // packed path: h (fp32, already halved) -> bf16x2, one MUFU.TANH per pair, m = h + h*tanh(h) as HFMA2; the dot
+          // with the gate / coordinate vector accumulates the widened halves in fp32
 #pragma unroll
-        for (int e = 0; e < 16; e += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
-          v[e + 0] = silu_scaled<kFast>(v[e + 0]); v[e + 1] = silu_scaled<kFast>(v[e + 1]);
-          v[e + 2] = silu_scaled<kFast>(v[e + 2]); v[e + 3] = silu_scaled<kFast>(v[e + 3]);
-          dotp[0] = fmaf(v[e + 0], w4.x, dotp[0]); dotp[1] = fmaf(v[e + 1], w4.y, dotp[1]);
-          dotp[2] = fmaf(v[e + 2], w4.z, dotp[2]); dotp[3] = fmaf(v[e + 3], w4.w, dotp[3]);
+          for (int e = 0; e < 16; e += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
+            uint32_t h2, t2, m2a, m2b;
+            h2 = pack_bf16x2(v[e + 0], v[e + 1]);
+            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
+            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(m2a) : "r"(h2), "r"(t2));
+            h2 = pack_bf16x2(v[e + 2], v[e + 3]);
+            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
+            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(m2b) : "r"(h2), "r"(t2));
+            dotp[0] = fmaf(__uint_as_float(m2a << 16), w4.x, dotp[0]);
+            dotp[1] = fmaf(__uint_as_float(m2a & 0xffff0000u), w4.y, dotp[1]);
+            dotp[2] = fmaf(__uint_as_float(m2b << 16), w4.z, dotp[2]);
+            dotp[3] = fmaf(__uint_as_float(m2b & 0xffff0000u), w4.w, dotp[3]);
+            if constexpr (kSegMma) {
+              ew[ch * 8 + (e >> 1)] = m2a;
+              ew[ch * 8 + (e >> 1) + 1] = m2b;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
+            v[e + 0] = silu_scaled<kFast>(v[e + 0]); v[e + 1] = silu_scaled<kFast>(v[e + 1]);
+            v[e + 2] = silu_scaled<kFast>(v[e + 2]); v[e + 3] = silu_scaled<kFast>(v[e + 3]);
+            dotp[0] = fmaf(v[e + 0], w4.x, dotp[0]); dotp[1] = fmaf(v[e + 1], w4.y, dotp[1]);
+            dotp[2] = fmaf(v[e + 2], w4.z, dotp[2]); dotp[3] = fmaf(v[e + 3], w4.w, dotp[3]);
+          }
         }
         if constexpr (kSegMma) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ew[ch * 8 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          // messages are already cached in ew (packed bf16)
         } else if constexpr (!kEquiv) {
           tmem_st16(trow + col0, v);
         }
@@ -749,7 +787,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
           auto readout = [&](int cb) {
             float v[16];
-            tmem_ld16(trow + EDGE_ACOL + (cb & 1) * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), v);
+            tmem_ld16(trow + cb * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), v);
             tmem_wait_ld();
             const int ch = (cb < 3) ? 112 * (r >> 5) + 32 * cb + (r & 31) : 112 * (r >> 4) + 96 + (r & 15);
             if (cb < 3 || r < 64) {
@@ -773,17 +811,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             tc_fence_before();
           };
           long long s0 = profiling ? clock64() : 0;
-          // Round cb stages block cb into staging buffer cb&1 and its MMA writes D2 buffer cb&1; before reusing either,
-          // wait for the MMA of round cb-2 and read its result out.
+          // Round cb stages block cb into staging buffer cb&1; before reusing a buffer wait for the MMA of round cb-2.
+          // The four results stay in TMEM and are read out together at the end.
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) {
             const int eb = cb & 1;
             if (cb >= 2) {
               mbar_wait(e_done(eb), (uint32_t)((it * 2 + ((cb - 2) >> 1)) & 1));
-              tc_fence_after();
               if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }  // wait for the segment-sum MMA
-              readout(cb - 2);
-              if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }  // D2 readout + stores
             }
             uint8_t* sbuf = scratch + eb * 2 * A_CHUNK_BYTES;
             if (cb < 3) {
@@ -812,14 +847,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             if (lane == 0) arrive_leader(e_full(eb));
             if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate + stage + fence + arrive
           }
-#pragma unroll 1
-          for (int cb = 2; cb < 4; ++cb) {
-            mbar_wait(e_done(cb & 1), (uint32_t)((it * 2 + (cb >> 1)) & 1));
-            tc_fence_after();
-            if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
-            readout(cb);
-            if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
-          }
+          mbar_wait(e_done(0), (uint32_t)((it * 2 + 1) & 1));
+          mbar_wait(e_done(1), (uint32_t)((it * 2 + 1) & 1));
+          tc_fence_after();
+          if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) readout(cb);
+          if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
         } else {
 #pragma unroll 1
         for (int ch = 0; ch < 7; ++ch) {
