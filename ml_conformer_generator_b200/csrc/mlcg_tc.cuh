@@ -247,7 +247,8 @@ struct EdgeSmemT {
   static constexpr int TRS_OFF = DOT_OFF + 4 * TILE_M * 4;      // [2][128][3] coordinate messages
   static constexpr int RID_OFF = TRS_OFF + 2 * TILE_M * 3 * 4;  // [2][128] float2 (d2, d0^2)
   static constexpr int RIG_OFF = RID_OFF + 2 * TILE_M * 8;      // [2][128] int  g | j<<8 | valid<<16
-  static constexpr int PROF_OFF = RIG_OFF + 2 * TILE_M * 4;         // 16 x int64 phase counters (diagnostics)
+  static constexpr int WV_OFF = RIG_OFF + 2 * TILE_M * 4;       // [448] gate / coordinate-head vector
+  static constexpr int PROF_OFF = WV_OFF + HP * 4;         // 16 x int64 phase counters (diagnostics)
   static constexpr int BAR_OFF = PROF_OFF + 128;
   static constexpr int TOTAL = BAR_OFF + 256;
   static constexpr int ALLOC = TOTAL + 1024;
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   float* trs_all = reinterpret_cast<float*>(gbase + EdgeSmem::TRS_OFF);
   float2* ri_d_all = reinterpret_cast<float2*>(gbase + EdgeSmem::RID_OFF);
   int* ri_gj_all = reinterpret_cast<int*>(gbase + EdgeSmem::RIG_OFF);
+  float* wv_s = reinterpret_cast<float*>(gbase + EdgeSmem::WV_OFF);
   uint8_t* scratch = gbase + EdgeSmem::SCR_OFF;
   const uint32_t bar0 = base + EdgeSmem::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) wv_s[i] = p.wv[i];
   if (warp == 1) {
     if constexpr (kPair) tmem_alloc_pair<512>(smem_u32(tmem_slot));
     else tmem_alloc<512>(smem_u32(tmem_slot));
@@ -701,18 +704,21 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       // thread (row r, quarter qq) owns output columns 112*qq .. 112*qq+111 in 7 runs of 16.  GCL bf16 mode keeps the
       // SiLU'd messages as packed bf16 in registers (ew) for pass 2; the other variants write them back to TMEM.
       uint32_t ew[kSegMma ? 56 : 1];
+      // software-pipelined TMEM reads: the load of run ch+1 is in flight while run ch is processed
+      float vbuf[2][16];
+      tmem_ld16(trow + qq * 112, vbuf[0]);
+      tmem_wait_ld();
 #pragma unroll
       for (int ch = 0; ch < 7; ++ch) {
         const int col0 = qq * 112 + ch * 16;  // warp-uniform
-        float v[16];
-        tmem_ld16(trow + col0, v);
-        tmem_wait_ld();
+        float* v = vbuf[ch & 1];
+        if (ch + 1 < 7) tmem_ld16(trow + col0 + 16, vbuf[(ch + 1) & 1]);
         if constexpr (kFast) {
           // packed path: h (fp32, already halved) -> bf16x2, one MUFU.TANH per pair, m = h + h*tanh(h) as HFMA2; the dot
           // with the gate / coordinate vector accumulates the widened halves in fp32
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
+            const float4 w4 = *reinterpret_cast<const float4*>(wv_s + col0 + e);
             uint32_t h2, t2, m2a, m2b;
             h2 = pack_bf16x2(v[e + 0], v[e + 1]);
             asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
@@ -732,7 +738,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         } else {
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&p.wv[col0 + e]);
+            const float4 w4 = *reinterpret_cast<const float4*>(wv_s + col0 + e);
             v[e + 0] = silu_scaled<kFast>(v[e + 0]); v[e + 1] = silu_scaled<kFast>(v[e + 1]);
             v[e + 2] = silu_scaled<kFast>(v[e + 2]); v[e + 3] = silu_scaled<kFast>(v[e + 3]);
             dotp[0] = fmaf(v[e + 0], w4.x, dotp[0]); dotp[1] = fmaf(v[e + 1], w4.y, dotp[1]);
@@ -744,6 +750,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         } else if constexpr (!kEquiv) {
           tmem_st16(trow + col0, v);
         }
+        if (ch + 1 < 7) tmem_wait_ld();
       }
       if constexpr (kSegMma) {  // D has been fully consumed: the next tile's MMAs may overwrite it
         tc_fence_before();
