@@ -557,7 +557,7 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
       GemmArgs b{};
       b.a0 = h->t_op.as<uint8_t>(); b.a0_chunks = kc; b.a0_per_tile = kc; b.n_kc = kc;
       b.w = L.w4_op.as<uint8_t>(); b.bias = L.b4p.as<float>(); b.m_rows = h->M;
-      b.out_op = h->h_op.as<uint8_t>(); b.out_op_chunks = kc; b.resid = h->h_res.as<float>(); b.ldr = HP;
+      b.out_op = h->h_op.as<uint8_t>(); b.out_op_chunks = kc; b.resid = h->h_res.as<float>(); b.ldr = 0;  // tiled residual layout
       CK((launch_gemm_mode<HP, EPI_RESID_OP>(mode, b, h->n_mtiles, 1, st)));
       h->launches++;
     }
@@ -632,11 +632,11 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
   const int kc = h->kc448();
   if (h->precision == PREC_BF16)
     k_egnn_prepare<PREC_BF16><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->w_emb.d,
-                                                  h->b_emb.d, h->h_res.as<float>(), HP, h->h_op.as<uint8_t>(), kc,
+                                                  h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
                                                   h->x0.as<float>(), h->xa.as<float>());
   else if (h->precision == PREC_TF32)
     k_egnn_prepare<PREC_TF32><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->w_emb.d,
-                                                  h->b_emb.d, h->h_res.as<float>(), HP, h->h_op.as<uint8_t>(), kc,
+                                                  h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
                                                   h->x0.as<float>(), h->xa.as<float>());
   else
     k_egnn_prepare<PREC_FP32_SIMT><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N,
@@ -646,7 +646,7 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
   int rc = (h->precision == PREC_FP32_SIMT) ? egnn_forward_simt(h, st) : egnn_forward_tc(h, st);
   if (rc) return rc;
   // 9 blocks: blocks 0,2,4,6,8 write xb -> final coordinates are in xb
-  k_egnn_readout<<<h->B, 128, 0, st>>>(h->h_res.as<float>(), HP, h->xb.as<float>(), h->x0.as<float>(), h->d_n_nodes.as<int>(),
+  k_egnn_readout<<<h->B, 128, 0, st>>>(h->h_res.as<float>(), h->precision == PREC_FP32_SIMT ? HP : 0, h->xb.as<float>(), h->x0.as<float>(), h->d_n_nodes.as<int>(),
                                        h->d_node_off.as<int>(), h->N, h->w_out.d, h->b_out.d, eps);
   KCHECK();
   return MLCG_OK;

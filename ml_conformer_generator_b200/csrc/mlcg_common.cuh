@@ -38,6 +38,14 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t p
   return r * 128u + ((p ^ (r & 7u)) << 4);
 }
 
+// fp32 residual stream h: index of (node, channel).  ldh > 0: row-major [node][ldh] (exact-fp32 SIMT path).
+// ldh == 0: tiled [node/128][channel/32][node%128][channel%32] -- in the tensor-core GEMM epilogue a thread owns one row
+// and 32 consecutive columns, so a warp touches 32 consecutive 128-byte segments (fully coalesced).
+__host__ __device__ __forceinline__ size_t hres_index(int node, int c, int ldh) {
+  return ldh > 0 ? (size_t)node * ldh + c
+                 : ((size_t)(node >> 7) * (HP / 32) + (c >> 5)) * (TILE_M * 32) + (size_t)(node & 127) * 32 + (c & 31);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // activations
 // ---------------------------------------------------------------------------------------------------------------

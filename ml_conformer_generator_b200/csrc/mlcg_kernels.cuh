@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(HP) k_egnn_prepare(const float* __restrict__ z
 #pragma unroll
     for (int k = 0; k < IN_NF; ++k) acc = fmaf(w_emb[c * IN_NF + k], hin[k], acc);
   }
-  h_res[(size_t)node * ldh + c] = acc;
+  h_res[hres_index(node, c, ldh)] = acc;
   if constexpr (kMode != PREC_FP32_SIMT) op_store1<kMode>(h_op, op_chunks, node, c, acc);
 }
 
@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(128) k_egnn_readout(const float* __restrict__ 
     const int i = d >> 3, o = d & 7;
     float acc = 0.f;
     if (i < n) {
-      const float* hr = h_res + (size_t)(node0 + i) * ldh;
-      for (int k = lane; k < HID; k += 32) acc = fmaf(w_out[o * HID + k], hr[k], acc);
+      for (int k = lane; k < HID; k += 32) acc = fmaf(w_out[o * HID + k], h_res[hres_index(node0 + i, k, ldh)], acc);
       acc = warp_sum(acc) + b_out[o];
     }
     if (lane == 0) eps[((size_t)b * N + i) * ZC + 3 + o] = acc;

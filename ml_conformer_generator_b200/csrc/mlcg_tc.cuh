@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
           }
           op_store<kMode, 32>(p.out_op, p.out_op_chunks, grow, gcol, v);
         } else {
-          float* rrow = p.resid + (size_t)grow * p.ldr + gcol;
+          float* rrow = p.resid + hres_index(grow, gcol, p.ldr);  // 32 consecutive floats in both layouts
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 b = __ldg(b4 + (e >> 2));
