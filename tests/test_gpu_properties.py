@@ -1,0 +1,101 @@
+"""GPU: size-independent properties of the denoiser on batches too large for the CPU oracle (ragged 15-39 atoms).
+
+* padding invariance: a sample's eps does not depend on N_max or on its neighbours in the batch (bit-exact per mode --
+  tiles never span molecules and the reduction order inside a molecule is fixed);
+* E(3) equivariance: rotating + translating the input coordinates rotates the predicted velocity and leaves the class
+  channels unchanged; permuting the atoms of a molecule permutes the output rows;
+* padded rows are exactly zero and the velocity is centre-of-gravity free.
+Tolerances: equivariance holds up to the mode's arithmetic (the rotated problem rounds differently): fp32 1e-4,
+tf32 2e-3, bf16 2e-2 relative L2."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from ml_conformer_generator_b200.config import CONTEXT_NORMS
+from oracle import edm_oracle as O
+
+pytestmark = pytest.mark.gpu
+EQ_TOL = {"fp32": 1e-4, "tf32": 2e-3, "bf16": 2e-2}
+
+
+def _batch(B, seed, n_max=39):
+    g = torch.Generator().manual_seed(seed)
+    n_nodes = torch.randint(15, 40, (B,), generator=g)
+    nm, _ = O.prepare_masks(n_nodes, n_max)
+    z = torch.randn(B, n_max, 11, generator=g) * nm
+    z[:, :, :3] *= 1.7
+    z[:, :, :3] = O.remove_mean_with_mask(z[:, :, :3], nm)
+    ctx = O.normalise_context(torch.tensor([53.6424, 108.3042, 151.4399]), CONTEXT_NORMS).view(1, 3).repeat(B, 1)
+    return n_nodes, nm, z, ctx, torch.full((B,), 0.42)
+
+
+def _rotation(seed):
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_padding_and_batch_invariance(engines, mode):
+    e = engines(mode)
+    n_nodes, nm, z, ctx, t = _batch(300, 1)
+    e.set_batch(n_nodes.numpy(), 39)
+    full = e.egnn_forward(t, z, ctx).cpu()
+    assert float(full[nm.squeeze(-1) == 0].abs().max()) == 0.0
+    com = (full[:, :, :3] * nm).sum(1).abs().max()
+    assert float(com) < 1e-3 * float(full[:, :, :3].abs().max())
+    # a sub-batch in a different order, padded to a smaller N_max, must give bit-identical rows
+    idx = torch.tensor([17, 3, 250, 99, 100, 101, 7])
+    n_max = int(n_nodes[idx].max())
+    e.set_batch(n_nodes[idx].numpy(), n_max)
+    sub = e.egnn_forward(t[idx], z[idx, :n_max].contiguous(), ctx[idx]).cpu()
+    assert torch.equal(sub, full[idx, :n_max])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_rotation_translation_permutation_equivariance(engines, mode):
+    e = engines(mode)
+    B = 64 if mode == "fp32" else 256
+    n_nodes, nm, z, ctx, t = _batch(B, 2)
+    e.set_batch(n_nodes.numpy(), 39)
+    base = e.egnn_forward(t, z, ctx).cpu()
+    rot = _rotation(5)
+    z2 = z.clone()
+    z2[:, :, :3] = (z[:, :, :3] @ rot.t() + torch.tensor([0.3, -1.1, 0.7])) * nm  # rotate + translate real atoms
+    out2 = e.egnn_forward(t, z2, ctx).cpu()
+    expect = base.clone()
+    expect[:, :, :3] = base[:, :, :3] @ rot.t()
+    err = rel_l2(out2, expect)
+    print("equivariance", mode, err)
+    assert err < EQ_TOL[mode]
+    # permutation of the atoms inside every molecule
+    z3, expect3 = z.clone(), base.clone()
+    g = torch.Generator().manual_seed(9)
+    for b in range(B):
+        n = int(n_nodes[b])
+        perm = torch.randperm(n, generator=g)
+        z3[b, :n] = z[b, perm]
+        expect3[b, :n] = base[b, perm]
+    out3 = e.egnn_forward(t, z3, ctx).cpu()
+    perr = rel_l2(out3, expect3)
+    print("permutation", mode, perr)
+    assert perr < EQ_TOL[mode]
+
+
+def test_full_size_generation_properties(engines):
+    """BASELINE config C2 shape (B=1024, 39 atoms) with a short schedule: finite outputs, valid classes / bond orders,
+    deterministic for a fixed seed, different for another seed."""
+    e = engines("bf16")
+    n_nodes = np.full(1024, 39, np.int32)
+    ctx = np.tile(np.asarray(O.normalise_context(torch.tensor([53.6424, 108.3042, 151.4399]), CONTEXT_NORMS)), (1024, 1))
+    a = [t.clone() for t in e.generate_host(n_nodes, 39, ctx, T=2, seed=1)]
+    b = [t.clone() for t in e.generate_host(n_nodes, 39, ctx, T=2, seed=1)]
+    c = [t.clone() for t in e.generate_host(n_nodes, 39, ctx, T=2, seed=2)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert not torch.equal(a[0], c[0])
+    assert torch.isfinite(a[0]).all() and int(a[1].min()) >= 0 and int(a[1].max()) <= 6
+    assert int(a[2].min()) >= 0 and int(a[2].max()) <= 4 and bool((torch.triu(a[2].long()) == 0).all())
+    assert float(a[0].mean(dim=1).abs().max()) < 0.5 * float(a[0].abs().max())
