@@ -86,6 +86,14 @@ struct mlcg_handle {
   DevBuf g_ctx, g_z, g_x, g_cls, g_el, g_dist, g_adj, g_bonds;
   // test gemm
   DevBuf tg_a, tg_w, tg_b, tg_c;
+  // CUDA-graph replay of mlcg_generate (whole reverse loop + GCN as one graph)
+  DevBuf noise_ctl;               // {seed, sample_offset} read by the noise kernels when use_noise_ctl is set
+  bool use_noise_ctl = false;
+  cudaGraphExec_t gen_graph = nullptr;
+  std::vector<long long> gen_key;  // geometry / schedule the graph was captured for
+  int gen_key_hits = 0;            // calls seen with the current key (1st runs eagerly, 2nd captures)
+  long long gen_graph_launches = 0;
+  cudaStream_t own_stream = nullptr;  // used by mlcg_generate when the caller passes the NULL stream (not capturable)
   int kc448() const { return HP / epc(precision == PREC_BF16 ? PREC_BF16 : PREC_TF32); }
 };
 
@@ -183,12 +191,13 @@ __global__ void k_fill_f32(float* p, float v, int n) {
   if (i < n) p[i] = v;
 }
 
-static NoiseSrc to_src(const mlcg_noise* n) {
+static NoiseSrc to_src(const mlcg_handle* h, const mlcg_noise* n) {
   NoiseSrc s;
   s.raw = n->raw;
   s.seed = n->seed;
   s.draw = n->draw;
   s.sample_offset = n->sample_offset;
+  s.ctl = (h->use_noise_ctl && n->raw == nullptr) ? h->noise_ctl.as<unsigned long long>() : nullptr;
   return s;
 }
 
@@ -224,6 +233,9 @@ extern "C" void mlcg_destroy(mlcg_handle* h) {
   for (auto& s : h->seer_gcn) { s.w_op.release(); s.b_pad.release(); }
   h->seer_resize.w_op.release();
   h->seer_resize.b_pad.release();
+  if (h->gen_graph) cudaGraphExecDestroy(h->gen_graph);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  h->noise_ctl.release();
   for (DevBuf* b : {&h->d_n_nodes, &h->d_node_off, &h->d_node_mol, &h->d_node_edge_off, &h->d_tiles, &h->x0, &h->xa, &h->xb,
                     &h->h_res, &h->pq, &h->h_op, &h->agg_op, &h->t_op, &h->agg_f32, &h->t_f32, &h->a1, &h->m2, &h->t_dev,
                     &h->eps_dev, &h->s_ld, &h->s_la, &h->s_rowd, &h->s_rowa, &h->s_x64, &h->s_y_op, &h->s_x, &h->s_emb,
@@ -412,6 +424,10 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   if (!h) return MLCG_E_ARG;
   if (!n_nodes || B <= 0 || N <= 0 || N > EDGE_MAXN) FAIL(MLCG_E_ARG, "set_batch: need B > 0 and 1 <= N <= 39");
   CK(cudaSetDevice(h->device));
+  // any change of the batch plan invalidates the graph captured by mlcg_generate
+  if (h->gen_graph) { cudaGraphExecDestroy(h->gen_graph); h->gen_graph = nullptr; }
+  h->gen_key.clear();
+  h->gen_key_hits = 0;
   h->batch_set = false;
   h->B = B;
   h->N = N;
@@ -665,7 +681,7 @@ static inline int warp_grid(int B) { return (B * 32 + 127) / 128; }
 extern "C" int mlcg_noise_init(mlcg_handle* h, float* z, const mlcg_noise* noise, void* stream) {
   STEP_PROLOGUE("noise_init");
   if (!z || !noise) FAIL(MLCG_E_ARG, "noise_init: null pointer");
-  k_noise_init<<<warp_grid(h->B), 128, 0, st>>>(z, h->d_n_nodes.as<int>(), h->B, h->N, to_src(noise));
+  k_noise_init<<<warp_grid(h->B), 128, 0, st>>>(z, h->d_n_nodes.as<int>(), h->B, h->N, to_src(h, noise));
   KCHECK();
   return MLCG_OK;
 }
@@ -674,7 +690,7 @@ extern "C" int mlcg_step(mlcg_handle* h, float* z, const float* eps, const mlcg_
   STEP_PROLOGUE("step");
   if (!z || !eps || !sc || !noise) FAIL(MLCG_E_ARG, "step: null pointer");
   k_step<<<warp_grid(h->B), 128, 0, st>>>(z, eps, h->d_n_nodes.as<int>(), h->B, h->N, sc->alpha_ts, sc->c_eps, sc->c_sigma,
-                                          to_src(noise));
+                                          to_src(h, noise));
   KCHECK();
   return MLCG_OK;
 }
@@ -683,7 +699,7 @@ extern "C" int mlcg_reinject(mlcg_handle* h, float* z, const float* z_known, con
   STEP_PROLOGUE("reinject");
   if (!z || !z_known || !fixed_mask || !sc || !noise) FAIL(MLCG_E_ARG, "reinject: null pointer");
   k_reinject<<<warp_grid(h->B), 128, 0, st>>>(z, z_known, fixed_mask, h->d_n_nodes.as<int>(), h->B, h->N, sc->alpha_s,
-                                              sc->sigma_s, sc->blend, to_src(noise));
+                                              sc->sigma_s, sc->blend, to_src(h, noise));
   KCHECK();
   return MLCG_OK;
 }
@@ -692,7 +708,7 @@ extern "C" int mlcg_forward_diffuse(mlcg_handle* h, float* z, const float* z_kno
   STEP_PROLOGUE("forward_diffuse");
   if (!z || !z_known || !noise) FAIL(MLCG_E_ARG, "forward_diffuse: null pointer");
   k_forward_diffuse<<<warp_grid(h->B), 128, 0, st>>>(z, z_known, h->d_n_nodes.as<int>(), h->B, h->N, alpha, sigma,
-                                                     to_src(noise));
+                                                     to_src(h, noise));
   KCHECK();
   return MLCG_OK;
 }
@@ -701,7 +717,7 @@ extern "C" int mlcg_decode(mlcg_handle* h, const float* z0, const float* eps0, f
   STEP_PROLOGUE("decode");
   if (!z0 || !eps0 || !noise || !x || !atom_class) FAIL(MLCG_E_ARG, "decode: null pointer");
   k_decode<<<warp_grid(h->B), 128, 0, st>>>(z0, eps0, h->d_n_nodes.as<int>(), h->B, h->N, sigma_0, alpha_0, sigma_x,
-                                            to_src(noise), x, atom_class);
+                                            to_src(h, noise), x, atom_class);
   KCHECK();
   return MLCG_OK;
 }
@@ -896,6 +912,21 @@ extern "C" int mlcg_seer_forward(mlcg_handle* h, const int32_t* elements, const 
 // ---------------------------------------------------------------------------------------------------------------
 // end-to-end with host buffers
 // ---------------------------------------------------------------------------------------------------------------
+// The device part of mlcg_generate: reverse loop + GCN inputs + GCN.  Pure kernel / async-copy sequence on `stream`
+// (no allocation, no synchronisation once the workspaces exist), hence capturable into a CUDA graph.
+static int generate_device(mlcg_handle* h, int T, const mlcg_step_scalars* steps, int resample_steps, float sigma_0,
+                           float alpha_0, float sigma_x, uint64_t seed, int64_t sample_offset, void* stream) {
+  int rc = mlcg_sample(h, 0, T, steps, resample_steps, 0, 0.f, 0.f, sigma_0, alpha_0, sigma_x, h->g_ctx.as<float>(), nullptr,
+                       nullptr, nullptr, seed, sample_offset, h->g_z.as<float>(), h->g_x.as<float>(), h->g_cls.as<int32_t>(),
+                       nullptr, nullptr, stream);
+  if (rc) return rc;
+  if ((rc = mlcg_seer_inputs(h, h->g_x.as<float>(), h->g_cls.as<int32_t>(), h->g_el.as<int32_t>(), h->g_dist.as<float>(),
+                             h->g_adj.as<float>(), stream)))
+    return rc;
+  return mlcg_seer_forward(h, h->g_el.as<int32_t>(), h->g_dist.as<float>(), h->g_adj.as<float>(), nullptr,
+                           h->g_bonds.as<int8_t>(), h->B, stream);
+}
+
 extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, const float* ctx_host, int T,
                              const mlcg_step_scalars* steps, int resample_steps, float sigma_0, float alpha_0, float sigma_x,
                              uint64_t seed, int64_t sample_offset, float* x_host, int32_t* atom_class_host,
@@ -904,8 +935,32 @@ extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B,
   if (!h->egnn_loaded || !h->seer_loaded) FAIL(MLCG_E_STATE, "generate: load both weight sets first");
   if (!n_nodes_host || !ctx_host || !steps || !x_host || !atom_class_host || !bonds_host) FAIL(MLCG_E_ARG, "generate: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = mlcg_set_batch(h, n_nodes_host, B, N);
-  if (rc) return rc;
+  if (st == nullptr) {
+    // the legacy NULL stream cannot be captured; the call is synchronous and takes host buffers, so run it on a
+    // private stream
+    if (h->own_stream == nullptr) CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
+    st = h->own_stream;
+    stream = (void*)st;
+  }
+  // Key of the captured graph: batch geometry, schedule and every scalar baked into kernel arguments.
+  std::vector<long long> key;
+  key.reserve((size_t)B + 8 * (size_t)T + 16);
+  key.push_back(B); key.push_back(N); key.push_back(T); key.push_back(resample_steps); key.push_back(h->precision);
+  auto bits = [](float f) { int32_t i; memcpy(&i, &f, 4); return (long long)i; };
+  key.push_back(bits(sigma_0)); key.push_back(bits(alpha_0)); key.push_back(bits(sigma_x));
+  for (int b = 0; b < B; ++b) key.push_back(n_nodes_host[b]);
+  for (int s = 0; s < T; ++s) {
+    key.push_back(bits(steps[s].t)); key.push_back(bits(steps[s].alpha_ts)); key.push_back(bits(steps[s].c_eps));
+    key.push_back(bits(steps[s].c_sigma));
+  }
+  const bool same = (key == h->gen_key);
+  if (!same) {
+    int rc = mlcg_set_batch(h, n_nodes_host, B, N);  // also drops any previously captured graph
+    if (rc) return rc;
+    h->gen_key = key;
+  }
+  h->gen_key_hits++;
   const size_t bn = (size_t)B * N, dd = (size_t)B * SEER_D * SEER_D;
   CK(h->g_ctx.ensure((size_t)B * 3 * 4));
   CK(h->g_z.ensure(bn * ZC * 4));
@@ -915,17 +970,47 @@ extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B,
   CK(h->g_dist.ensure(dd * 4));
   CK(h->g_adj.ensure(dd * 4));
   CK(h->g_bonds.ensure(dd));
+  CK(h->noise_ctl.ensure(2 * sizeof(unsigned long long)));
+  static int graphs_enabled = -1;
+  if (graphs_enabled < 0) {
+    const char* e = getenv("MLCG_GRAPH");
+    graphs_enabled = (e == nullptr) ? 1 : (atoi(e) != 0);
+  }
   CK(cudaMemcpyAsync(h->g_ctx.p, ctx_host, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
-  rc = mlcg_sample(h, 0, T, steps, resample_steps, 0, 0.f, 0.f, sigma_0, alpha_0, sigma_x, h->g_ctx.as<float>(), nullptr,
-                   nullptr, nullptr, seed, sample_offset, h->g_z.as<float>(), h->g_x.as<float>(), h->g_cls.as<int32_t>(),
-                   nullptr, nullptr, stream);
+  const unsigned long long ctl[2] = {(unsigned long long)seed, (unsigned long long)sample_offset};
+  CK(cudaMemcpyAsync(h->noise_ctl.p, ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+  int rc = MLCG_OK;
+  h->use_noise_ctl = true;  // the noise kernels read {seed, sample_offset} from device memory (graph-replayable)
+  if (graphs_enabled && h->gen_graph == nullptr && h->gen_key_hits >= 2) {
+    // second call with this geometry: all workspaces exist and every kernel attribute has been set by the eager
+    // first call, so the launch sequence can be captured
+    cudaGraph_t graph = nullptr;
+    const long long launches0 = h->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = generate_device(h, T, steps, resample_steps, sigma_0, alpha_0, sigma_x, seed, sample_offset, stream);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc == MLCG_OK && ce == cudaSuccess && graph != nullptr) {
+      ce = cudaGraphInstantiate(&h->gen_graph, graph, 0);
+      if (ce != cudaSuccess) h->gen_graph = nullptr;
+    }
+    if (graph) cudaGraphDestroy(graph);
+    h->gen_graph_launches = h->launches - launches0;
+    h->launches = launches0;  // nothing has run yet
+    if (rc != MLCG_OK || h->gen_graph == nullptr) {
+      cudaGetLastError();
+      h->use_noise_ctl = false;
+      if (rc == MLCG_OK) FAIL(MLCG_E_STATE, "generate: CUDA graph capture failed");
+      return rc;
+    }
+  }
+  if (h->gen_graph != nullptr) {
+    CK(cudaGraphLaunch(h->gen_graph, st));
+    h->launches += h->gen_graph_launches;
+  } else {
+    rc = generate_device(h, T, steps, resample_steps, sigma_0, alpha_0, sigma_x, seed, sample_offset, stream);
+  }
+  h->use_noise_ctl = false;
   if (rc) return rc;
-  if ((rc = mlcg_seer_inputs(h, h->g_x.as<float>(), h->g_cls.as<int32_t>(), h->g_el.as<int32_t>(), h->g_dist.as<float>(),
-                             h->g_adj.as<float>(), stream)))
-    return rc;
-  if ((rc = mlcg_seer_forward(h, h->g_el.as<int32_t>(), h->g_dist.as<float>(), h->g_adj.as<float>(), nullptr,
-                              h->g_bonds.as<int8_t>(), B, stream)))
-    return rc;
   CK(cudaMemcpyAsync(x_host, h->g_x.p, bn * 3 * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(atom_class_host, h->g_cls.p, bn * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(bonds_host, h->g_bonds.p, dd, cudaMemcpyDeviceToHost, st));

@@ -16,6 +16,8 @@ struct NoiseSrc {
   unsigned long long seed;     // device Philox otherwise: keyed by (seed, global sample id, atom, draw index)
   unsigned long long draw;
   long long sample_offset;     // global id of sample 0 of this shard (shard-invariant sampling)
+  const unsigned long long* ctl;  // optional device pointer to {seed, sample_offset}: overrides the two fields above so a
+                                  // captured CUDA graph can be replayed with new seeds
 };
 
 // Raw draws for atom i of sample b (11 values: 3 position + 8 feature; reference order
@@ -27,7 +29,9 @@ __device__ __forceinline__ void raw_noise(const NoiseSrc& ns, int b, int i, int 
     for (int c = 0; c < ZC; ++c) out[c] = src[c];
   } else {
     curandStatePhilox4_32_10_t st;
-    curand_init(ns.seed, (unsigned long long)(ns.sample_offset + b) * 64ull + (unsigned long long)i, ns.draw * 3ull, &st);
+    const unsigned long long seed = ns.ctl ? ns.ctl[0] : ns.seed;
+    const long long off = ns.ctl ? (long long)ns.ctl[1] : ns.sample_offset;
+    curand_init(seed, (unsigned long long)(off + b) * 64ull + (unsigned long long)i, ns.draw * 3ull, &st);
     const float4 a = curand_normal4(&st), c = curand_normal4(&st), d = curand_normal4(&st);
     out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
     out[4] = c.x; out[5] = c.y; out[6] = c.z; out[7] = c.w;
