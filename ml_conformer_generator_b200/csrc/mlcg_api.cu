@@ -77,7 +77,8 @@ struct mlcg_handle {
   long long n_edges = 0;
   std::vector<int> h_n_nodes, h_node_off;
   std::vector<SimtChunk> simt_chunks;
-  DevBuf d_n_nodes, d_node_off, d_node_mol, d_node_edge_off, d_tiles;
+  DevBuf d_n_nodes, d_node_off, d_node_mol, d_node_edge_off, d_tiles, d_fix_node, fix_agg, fix_dx;
+  int n_fix = 0;  // target nodes whose neighbour list is split over two edge tiles
   // EGNN workspaces
   DevBuf x0, xa, xb, h_res, pq, h_op, agg_op, t_op, agg_f32, t_f32, a1, m2, t_dev, eps_dev;
   // seer workspaces
@@ -161,6 +162,16 @@ static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair>, a);
 }
+// Edge tiles are 128-row ranges of a molecule's edge list that may split a target node's neighbours over two tiles
+// (default); MLCG_EDGE_SPLIT=0 keeps whole targets per tile (lower row occupancy, no fix-up kernel).
+static bool edge_split_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLCG_EDGE_SPLIT");
+    v = (e == nullptr) ? 1 : (atoi(e) != 0);
+  }
+  return v != 0;
+}
 // CTA-pair mode (default) needs an even grid; MLCG_EDGE_PAIR=0 selects the single-CTA kernel.
 static bool edge_pair_mode() {
   static int v = -1;
@@ -180,6 +191,29 @@ static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int
   if (pair) return equiv ? launch_edge<PREC_TF32, true, true>(a, grid, st) : launch_edge<PREC_TF32, false, true>(a, grid, st);
   return equiv ? launch_edge<PREC_TF32, true, false>(a, grid, st) : launch_edge<PREC_TF32, false, false>(a, grid, st);
 }
+// second half of an edge layer: completes the targets whose neighbour list is split over two tiles
+static cudaError_t launch_edge_fixup(mlcg_handle* h, int mode, bool equiv, const EdgeArgs& a, cudaStream_t st) {
+  if (h->n_fix == 0) return cudaSuccess;
+  const int* fn = h->d_fix_node.as<int>();
+  if (equiv) {
+    const int grid = (h->n_fix * 4 + 127) / 128;
+    if (mode == PREC_BF16)
+      k_edge_fixup<PREC_BF16, true><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
+    else
+      k_edge_fixup<PREC_TF32, true><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
+  } else {
+    if (mode == PREC_BF16) {
+      const int grid = (h->n_fix * (HP / epp(PREC_BF16)) + 127) / 128;
+      k_edge_fixup<PREC_BF16, false><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
+    } else {
+      const int grid = (h->n_fix * (HP / epp(PREC_TF32)) + 127) / 128;
+      k_edge_fixup<PREC_TF32, false><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
+    }
+  }
+  h->launches++;
+  return cudaGetLastError();
+}
+
 static cudaError_t launch_pack(int mode, const PackArgs& a, int n_ntiles, cudaStream_t st) {
   dim3 grid(a.n_kc, n_ntiles);
   if (mode == PREC_BF16) k_pack_weight<PREC_BF16><<<grid, 256, 0, st>>>(a);
@@ -236,7 +270,7 @@ extern "C" void mlcg_destroy(mlcg_handle* h) {
   if (h->gen_graph) cudaGraphExecDestroy(h->gen_graph);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   h->noise_ctl.release();
-  for (DevBuf* b : {&h->d_n_nodes, &h->d_node_off, &h->d_node_mol, &h->d_node_edge_off, &h->d_tiles, &h->x0, &h->xa, &h->xb,
+  for (DevBuf* b : {&h->d_n_nodes, &h->d_node_off, &h->d_node_mol, &h->d_node_edge_off, &h->d_tiles, &h->d_fix_node, &h->fix_agg, &h->fix_dx, &h->x0, &h->xa, &h->xb,
                     &h->h_res, &h->pq, &h->h_op, &h->agg_op, &h->t_op, &h->agg_f32, &h->t_f32, &h->a1, &h->m2, &h->t_dev,
                     &h->eps_dev, &h->s_ld, &h->s_la, &h->s_rowd, &h->s_rowa, &h->s_x64, &h->s_y_op, &h->s_x, &h->s_emb,
                     &h->s_add, &h->s_raw, &h->s_y_f32, &h->g_ctx, &h->g_z, &h->g_x, &h->g_cls, &h->g_el, &h->g_dist,
@@ -434,14 +468,37 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   h->h_n_nodes.assign(n_nodes, n_nodes + B);
   h->h_node_off.assign(B + 1, 0);
   std::vector<int> node_mol, node_edge_off;
-  std::vector<int4> tiles;
+  std::vector<EdgeTile> tiles;
+  std::vector<int> fix_node;
   long long edges = 0;
   for (int b = 0; b < B; ++b) {
     const int n = n_nodes[b];
     if (n < 1 || n > N) FAIL(MLCG_E_ARG, "set_batch: n_nodes[b] must be in [1, N]");
     h->h_node_off[b + 1] = h->h_node_off[b] + n;
-    const int gmax = std::min(EDGE_MAXG, n > 1 ? TILE_M / (n - 1) : EDGE_MAXG);
-    for (int i0 = 0; i0 < n; i0 += gmax) tiles.push_back(make_int4(b, i0, std::min(gmax, n - i0), n));
+    const int nm1 = n - 1, node0 = h->h_node_off[b];
+    if (nm1 < EDGE_MAXG || !edge_split_mode()) {
+      // few neighbours per target: whole targets per tile (a 128-row window could touch more than EDGE_MAXG targets)
+      const int gmax = std::min(EDGE_MAXG, n > 1 ? TILE_M / nm1 : EDGE_MAXG);
+      for (int i0 = 0; i0 < n; i0 += gmax) {
+        const int ng = std::min(gmax, n - i0);
+        tiles.push_back(EdgeTile{b, 0, ng * nm1, n, i0, ng, -1, -1});
+      }
+    } else {
+      // cut the n(n-1) target-major edge rows into near-equal ranges of at most 128 rows
+      const int E = n * nm1, T = (E + TILE_M - 1) / TILE_M;
+      int carry = -1;  // split-target id shared with the previous tile
+      for (int k = 0; k < T; ++k) {
+        const int ra = (int)((long long)k * E / T), rb = (int)((long long)(k + 1) * E / T);
+        const int i_first = ra / nm1, i_last = (rb - 1) / nm1;
+        EdgeTile t{b, ra - i_first * nm1, rb - ra, n, i_first, i_last - i_first + 1, carry, -1};
+        if (rb % nm1 != 0) {
+          t.fixb = (int)fix_node.size();
+          fix_node.push_back(node0 + i_last);
+        }
+        carry = t.fixb;
+        tiles.push_back(t);
+      }
+    }
     for (int i = 0; i < n; ++i) {
       node_mol.push_back(b);
       if (edges + (long long)i * (n - 1) > 0x7fffffffLL) FAIL(MLCG_E_ARG, "set_batch: too many edges for one batch");
@@ -458,12 +515,20 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   CK(h->d_node_off.ensure((B + 1) * sizeof(int)));
   CK(h->d_node_mol.ensure(h->M * sizeof(int)));
   CK(h->d_node_edge_off.ensure(h->M * sizeof(int)));
-  CK(h->d_tiles.ensure(tiles.size() * sizeof(int4)));
+  CK(h->d_tiles.ensure(tiles.size() * sizeof(EdgeTile)));
+  h->n_fix = (int)fix_node.size();
+  CK(h->d_fix_node.ensure(std::max<size_t>(fix_node.size(), 1) * sizeof(int)));
+  CK(h->fix_agg.ensure(std::max<size_t>(fix_node.size(), 1) * HP * sizeof(float)));
+  CK(h->fix_dx.ensure(std::max<size_t>(fix_node.size(), 1) * 4 * sizeof(float)));
   CK(cudaMemcpy(h->d_n_nodes.p, n_nodes, B * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_node_off.p, h->h_node_off.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_node_mol.p, node_mol.data(), h->M * sizeof(int), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_node_edge_off.p, node_edge_off.data(), h->M * sizeof(int), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_tiles.p, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_tiles.p, tiles.data(), tiles.size() * sizeof(EdgeTile), cudaMemcpyHostToDevice));
+  if (h->n_fix) CK(cudaMemcpy(h->d_fix_node.p, fix_node.data(), fix_node.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // the side buffers of split targets are zero between edge-kernel launches (k_edge_fixup re-zeroes what it consumes)
+  CK(cudaMemset(h->fix_agg.p, 0, std::max<size_t>(fix_node.size(), 1) * HP * sizeof(float)));
+  CK(cudaMemset(h->fix_dx.p, 0, std::max<size_t>(fix_node.size(), 1) * 4 * sizeof(float)));
   // workspaces (zero-initialised on growth; padded rows / columns are never written afterwards)
   CK(h->x0.ensure(mpad * 3 * sizeof(float)));
   CK(h->xa.ensure(mpad * 3 * sizeof(float)));
@@ -521,6 +586,8 @@ static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, f
   EdgeArgs a{};
   a.tiles = h->d_tiles.as<int4>();
   a.n_tiles = h->n_etiles;
+  a.fix_agg = h->fix_agg.as<float>();
+  a.fix_dx = h->fix_dx.as<float>();
   a.node_off = h->d_node_off.as<int>();
   a.pq = h->pq.p;
   a.x_cur = x_cur;
@@ -562,6 +629,7 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
     EdgeArgs ea = edge_args(h, L, x_cur, x_next);
     CK(launch_edge_mode(mode, L.equiv, ea, grid_e, st));
     h->launches++;
+    CK(launch_edge_fixup(h, mode, L.equiv, ea, st));
     if (!L.equiv) {
       GemmArgs a{};
       a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc;
@@ -1037,7 +1105,8 @@ extern "C" float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, voi
     h->launches++;
   }
   cudaEventRecord(e1, st);
-  if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+  if (launch_edge_fixup(h, h->precision, L.equiv, ea, st) != cudaSuccess) return -1.f;  // clears the split-target buffers
+  if (cudaEventSynchronize(e1) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return -1.f;
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
@@ -1060,6 +1129,7 @@ extern "C" int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, v
   ea.prof = buf.as<long long>();
   CK(launch_edge_mode(h->precision, L.equiv, ea, grid_e, st));
   h->launches++;
+  CK(launch_edge_fixup(h, h->precision, L.equiv, ea, st));
   std::vector<long long> host((size_t)grid_e * 16);
   CK(cudaMemcpyAsync(host.data(), buf.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -254,9 +254,22 @@ struct EdgeSmemT {
   static constexpr int ALLOC = TOTAL + 1024;
 };
 
+// One 128-row tile of the edge list of a molecule.  The n(n-1) real edges of a molecule are enumerated target-major
+// (target i, then its n-1 neighbours in ascending order) and cut into ceil(n(n-1)/128) near-equal row ranges, so a tile
+// may start and end in the middle of a target node's neighbour list.  Such a "split" target gets its neighbour sum from
+// two tiles: both add their partial sum into a per-batch fp32 side buffer (exactly two addends onto zero: the result does
+// not depend on their order) and k_edge_fixup turns it into the regular output afterwards.
+struct EdgeTile {
+  int mol, off0, nrows, n;   // molecule; neighbours of the first target that precede this tile; rows; atoms
+  int i0, ng, fixa, fixb;    // first target; targets touched; split-target ids of the first / last target or -1
+};
+static_assert(sizeof(EdgeTile) == 32, "EdgeTile is fetched as two int4");
+
 struct EdgeArgs {
-  const int4* tiles;   // {molecule, first target node i0, groups ng, atoms N}
+  const int4* tiles;   // [n_tiles] EdgeTile
   int n_tiles;
+  float* fix_agg;      // [n_fix][448] partial neighbour sums of split targets (GCL), zero between launches
+  float* fix_dx;       // [n_fix][4]   partial coordinate updates of split targets (equivariant layer)
   const int* node_off; // [B+1] prefix sum of atom counts
   const void* pq;      // [nodes][896] (fp32, or bf16 in bf16 mode): P = W1a.h at 0..447, Q = W1b.h + b1 at 448..895
   const float* x_cur;  // [nodes][3] coordinates at block start
@@ -374,13 +387,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     t_end = (int)(((long long)(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
     n_iter = t_end - t_begin;
   }
-  auto fetch_tile = [&](int it) -> int4 {
+  auto fetch_tile = [&](int it) -> EdgeTile {
     const int t = t_begin + it;
-    if (t < t_end) return p.tiles[t];
-    int4 g = p.tiles[t_end - 1 >= 0 ? max(t_end - 1, 0) : 0];  // ghost: same molecule, no target atoms
-    g.y = 0;
-    g.z = 0;
-    return g;
+    const int tt = t < t_end ? t : max(t_end - 1, 0);
+    const int4 a = p.tiles[2 * tt], b = p.tiles[2 * tt + 1];
+    EdgeTile e{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (t >= t_end) {  // ghost: same molecule, no rows, no target atoms
+      e.nrows = 0;
+      e.ng = 0;
+      e.fixa = e.fixb = -1;
+    }
+    return e;
   };
   constexpr int NARR = kPair ? 2 * (EDGE_CT / 32) : (EDGE_CT / 32);  // arrivals on the barriers the MMA issuer waits on
 
@@ -426,8 +443,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       int prev_mol = -1;
       uint32_t wi = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int4 ti = fetch_tile(it);
-        const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
+        const EdgeTile ti = fetch_tile(it);
+        const int mol = ti.mol, i0 = ti.i0, ng = ti.ng, n = ti.n;
         const int node0 = p.node_off[mol];
         mbar_wait(pq_empty, (uint32_t)((it & 1) ^ 1));
         const bool newmol = (mol != prev_mol);
@@ -564,16 +581,15 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       for (int k = 0; k < 16; ++k) pacc[k] = 0;
     // Row metadata (d2, d0^2, group / neighbour ids, unit vectors) and the group selector of a tile are double-buffered:
     // they are computed for tile it+1 while tile it waits for its last MMAs.
-    auto tile_setup = [&](const int4 ti, int buf) {
-      const int i0 = ti.y, ng = ti.z, n = ti.w;
+    auto tile_setup = [&](const EdgeTile ti, int buf) {
+      const int i0 = ti.i0, n = ti.n, off0 = ti.off0, nrows = ti.nrows;
       const int nm1 = max(n - 1, 1);
-      const int nrows = ng * (n - 1);
-      const int node0 = p.node_off[ti.x];
+      const int node0 = p.node_off[ti.mol];
       if (ct < TILE_M) {
         const int rr = ct;
         const bool rvalid = rr < nrows;
-        const int g = rvalid ? rr / nm1 : 0;
-        const int jj = rvalid ? rr - g * nm1 : 0;
+        const int g = rvalid ? (off0 + rr) / nm1 : 0;
+        const int jj = rvalid ? off0 + rr - g * nm1 : 0;
         const int i = i0 + g;
         const int j = rvalid ? jj + (jj >= i ? 1 : 0) : 0;
         const float* xi = p.x_cur + (size_t)(node0 + i) * 3;
@@ -595,7 +611,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         // S[g][k] = 1 if tile row k belongs to target node g: thread = (group g, 16-byte piece of 8 rows)
         if (ct >= 256) {
           const int g = (ct - 256) >> 4, piece = ct & 15;
-          const int lo_k = g * nm1, hi_k = min(lo_k + n - 1, nrows);  // rows [lo_k, hi_k) belong to group g
+          const int lo_k = max(g * nm1 - off0, 0), hi_k = min((g + 1) * nm1 - off0, nrows);  // rows of group g (may be empty)
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -613,11 +629,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     named_bar_sync(1, EDGE_CT);
     for (int it = 0; it < n_iter; ++it) {
       long long c0 = profiling ? clock64() : 0;
-      const int4 ti = fetch_tile(it);
-      const int mol = ti.x, i0 = ti.y, ng = ti.z, n = ti.w;
+      const EdgeTile ti = fetch_tile(it);
+      const int mol = ti.mol, i0 = ti.i0, ng = ti.ng, n = ti.n;
       const int nm1 = max(n - 1, 1);
       const int node0 = p.node_off[mol];
       const int buf = it & 1;
+      // rows [glo(g), ghi(g)) of this tile belong to target i0+g; gfix(g) = split-target id if its list continues in a
+      // neighbouring tile
+      auto glo = [&](int g) { return max(g * nm1 - ti.off0, 0); };
+      auto ghi = [&](int g) { return min((g + 1) * nm1 - ti.off0, ti.nrows); };
+      auto gfix = [&](int g) { return (g == 0 && ti.fixa >= 0) ? ti.fixa : (g == ng - 1) ? ti.fixb : -1; };
       float* trs = trs_all + buf * TILE_M * 3;
       const float2* ri_d = ri_d_all + buf * TILE_M;
       const int* ri_gj = ri_gj_all + buf * TILE_M;
@@ -775,9 +796,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         if (ct < ng * 3) {
           const int gg = ct / 3, c = ct - gg * 3;
           float s = 0.f;
-          for (int e = 0; e < n - 1; ++e) s += trs[(gg * nm1 + e) * 3 + c];
+          for (int e = glo(gg); e < ghi(gg); ++e) s += trs[e * 3 + c];
+          const int fx = gfix(gg);
           const size_t idx = (size_t)(node0 + i0 + gg) * 3 + c;
-          p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
+          if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
+          else p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
         }
         named_bar_sync(1, EDGE_CT);
       } else {
@@ -811,7 +834,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
                   const float val = (gi == 0) ? (qq == 0 ? v[0] : qq == 1 ? v[1] : qq == 2 ? v[2] : v[3])
                                   : (gi == 1) ? (qq == 0 ? v[4] : qq == 1 ? v[5] : qq == 2 ? v[6] : v[7])
                                               : (qq == 0 ? v[8] : qq == 1 ? v[9] : qq == 2 ? v[10] : v[11]);
-                  *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
+                  const int fx = gfix(g);
+                  if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + ch, val);
+                  else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
                 }
               }
             }
@@ -886,7 +911,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           for (int pr = cw; pr < 2 * ng; pr += 16) {
             const int hh = pr & 1, gg = pr >> 1;
             const uint8_t* src = scratch + hh * A_CHUNK_BYTES + (lane & 3) * 4;
-            const int r0 = gg * nm1, cnt = n - 1;
+            const int r0 = glo(gg), cnt = ghi(gg) - r0;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
             int e = 0;
             for (; e + 3 < cnt; e += 4) {
@@ -897,7 +922,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             }
             for (; e < cnt; ++e) s0 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e, lane >> 2));
             const int col = (2 * hh + (lane >> 4)) * 112 + ch * 16 + (lane & 15);
-            op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, col, ((s0 + s1) + (s2 + s3)) / 100.0f);
+            const int fx = gfix(gg);
+            if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + col, (s0 + s1) + (s2 + s3));
+            else op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, col, ((s0 + s1) + (s2 + s3)) / 100.0f);
           }
         }
         }
@@ -915,6 +942,42 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
   } else {
     if (warp == 1) tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Completes the split targets of an edge-kernel launch: their two partial sums have been added into the side buffer;
+// write the regular output (aggregate in operand format, or the coordinate update) and re-zero the buffer.
+template <int kMode, bool kEquiv>
+__global__ void k_edge_fixup(const int* __restrict__ fix_node, int n_fix, float* fix_agg, float* fix_dx, uint8_t* agg_op,
+                             int agg_chunks, const float* __restrict__ x_cur, float* x_next) {
+  if constexpr (kEquiv) {
+    // thread = (split target, coordinate)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = t >> 2, c = t & 3;
+    if (f < n_fix && c < 3) {
+      const size_t idx = (size_t)fix_node[f] * 3 + c;
+      const float s = fix_dx[(size_t)f * 4 + c];
+      fix_dx[(size_t)f * 4 + c] = 0.f;
+      x_next[idx] = x_cur[idx] + s / 100.0f;
+    }
+  } else {
+    // thread = (split target, 16-byte piece of the operand row): EPP channels -> one vector store
+    constexpr int EPP = epp(kMode), NP = HP / EPP;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = t / NP, pc = t - f * NP;
+    if (f >= n_fix) return;
+    const int node = fix_node[f];
+    float* src = fix_agg + (size_t)f * HP + pc * EPP;
+    float v[EPP];
+#pragma unroll
+    for (int e = 0; e < EPP; e += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(src + e);
+      *reinterpret_cast<float4*>(src + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
+    }
+#pragma unroll
+    for (int e = 0; e < EPP; ++e) v[e] = (kMode == PREC_BF16) ? v[e] * 0.01f : v[e] / 100.0f;
+    op_store<kMode, EPP>(agg_op, agg_chunks, node, pc * EPP, v);
   }
 }
 
