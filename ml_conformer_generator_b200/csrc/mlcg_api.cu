@@ -598,6 +598,17 @@ static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, f
   memcpy(a.wc, L.h_wc, sizeof(a.wc));
   memcpy(a.wd, L.h_wd, sizeof(a.wd));
   memcpy(a.wv, L.h_wv, sizeof(a.wv));
+  if (h->precision == PREC_BF16) {
+    auto bf = [](float f) -> uint32_t {  // round-to-nearest-even bf16 bits
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+    };
+    for (int k2 = 0; k2 < HP / 2; ++k2) {
+      a.wcd_h[4 * (k2 / 2) + (k2 & 1)] = bf(L.h_wc[2 * k2]) | (bf(L.h_wc[2 * k2 + 1]) << 16);
+      a.wcd_h[4 * (k2 / 2) + 2 + (k2 & 1)] = bf(L.h_wd[2 * k2]) | (bf(L.h_wd[2 * k2 + 1]) << 16);
+    }
+  }
   a.att_bias = L.att_bias;
   a.agg_op = h->agg_op.as<uint8_t>();
   a.agg_chunks = h->kc448();

@@ -284,6 +284,8 @@ struct EdgeArgs {
   alignas(16) float wc[HP];  // first-layer column for d2 (W1[:,840]), zero padded     } constant bank
   alignas(16) float wd[HP];  // first-layer column for d0^2 (W1[:,841])                 }
   alignas(16) float wv[HP];  // attention vector (GCL) or coordinate head (equivariant) }
+  alignas(16) uint32_t wcd_h[HP];  // bf16 mode: {wc[2k], wc[2k+1]} packed bf16x2 at [4*(k/2) + (k&1)],
+                                   //            {wd[2k], wd[2k+1]} at [4*(k/2) + 2 + (k&1)]  (one 128-bit load = 4 channels of both)
 };
 
 // CTA-pair variants (cta_group::2): issued by the leader CTA only; M = 256 spans both CTAs' TMEM, B is split in N
@@ -647,6 +649,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       const float2 rd = ri_d[r];
       const uint8_t* Prow = Ps + (info & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;  // invalid rows read row 0
       const uint8_t* Qrow = Qs + ((info >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
+      const uint32_t d2h = pack_bf16x2(rd.x, rd.x), d02h = pack_bf16x2(rd.y, rd.y);  // bf16 mode: packed distance features
       mbar_wait(pq_full, (uint32_t)(it & 1));
       if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
@@ -655,31 +658,25 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
         const int as = ai % EDGE_NA;
         const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
-        float wcv[ELEMS], wdv[ELEMS];  // 128-bit constant-bank loads (k0 is a multiple of 8)
-#pragma unroll
-        for (int e = 0; e < ELEMS; e += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(&p.wc[k0 + e]);
-          const float4 d4 = *reinterpret_cast<const float4*>(&p.wd[k0 + e]);
-          wcv[e] = c4.x; wcv[e + 1] = c4.y; wcv[e + 2] = c4.z; wcv[e + 3] = c4.w;
-          wdv[e] = d4.x; wdv[e + 1] = d4.y; wdv[e + 2] = d4.z; wdv[e + 3] = d4.w;
-        }
         uint32_t w[8];
         if constexpr (kPqBf16) {
-          // bf16 fast mode: everything after the fp32 distance terms is packed bf16x2 -- P+Q (HADD2), tanh (one MUFU
-          // per pair) and h + h*tanh(h) (HFMA2); the result is directly the packed A-operand word.
+          // bf16 fast mode: the whole pre-activation is packed bf16x2 math -- P+Q (HADD2), the two distance terms
+          // (HFMA2 with d2 / d0^2 rounded to bf16), tanh and h + h*tanh(h) (HFMA2); the result is directly the packed
+          // A-operand word.  wc / wd come from the constant bank as packed bf16x2 (warp-uniform index).
 #pragma unroll
           for (int e = 0; e < ELEMS; e += 8) {
             const uint4 pw = *reinterpret_cast<const uint4*>(Prow + (kc * EPC + e) * 2);
             const uint4 qw = *reinterpret_cast<const uint4*>(Qrow + (kc * EPC + e) * 2);
+            const uint4 c0 = *reinterpret_cast<const uint4*>(&p.wcd_h[(k0 + e)]);      // channels k0+e .. +3: wc, wc, wd, wd
+            const uint4 c1 = *reinterpret_cast<const uint4*>(&p.wcd_h[(k0 + e) + 4]);  // channels k0+e+4 .. +7
             const uint32_t pa[4] = {pw.x, pw.y, pw.z, pw.w}, qa[4] = {qw.x, qw.y, qw.z, qw.w};
+            const uint32_t wcp[4] = {c0.x, c0.y, c1.x, c1.y}, wdp[4] = {c0.z, c0.w, c1.z, c1.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint32_t sum, h2, t2, a2;
-              asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(sum) : "r"(pa[i]), "r"(qa[i]));
-              const int k = e + 2 * i;
-              const float h_lo = fmaf(rd.y, wdv[k], fmaf(rd.x, wcv[k], __uint_as_float(sum << 16)));
-              const float h_hi = fmaf(rd.y, wdv[k + 1], fmaf(rd.x, wcv[k + 1], __uint_as_float(sum & 0xffff0000u)));
-              h2 = pack_bf16x2(h_lo, h_hi);
+              uint32_t h2, t2, a2;
+              asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(h2) : "r"(pa[i]), "r"(qa[i]));
+              asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(h2) : "r"(d2h), "r"(wcp[i]));
+              asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(h2) : "r"(d02h), "r"(wdp[i]));
               asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
               asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a2) : "r"(h2), "r"(t2));
               w[(e >> 1) + i] = a2;
@@ -688,6 +685,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416): low half of word 2
           if (k0 == BIAS_COL - 4) w[2] = (w[2] & 0xffff0000u) | 0x3f80u;
         } else {
+          float wcv[ELEMS], wdv[ELEMS];  // 128-bit constant-bank loads (k0 is a multiple of 8)
+#pragma unroll
+          for (int e = 0; e < ELEMS; e += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(&p.wc[k0 + e]);
+            const float4 d4 = *reinterpret_cast<const float4*>(&p.wd[k0 + e]);
+            wcv[e] = c4.x; wcv[e + 1] = c4.y; wcv[e + 2] = c4.z; wcv[e + 3] = c4.w;
+            wdv[e] = d4.x; wdv[e + 1] = d4.y; wdv[e + 2] = d4.z; wdv[e + 3] = d4.w;
+          }
           float a[ELEMS];
 #pragma unroll
           for (int e = 0; e < ELEMS; e += 4) {
@@ -705,12 +710,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         long long cw0 = profiling ? clock64() : 0;
         mbar_wait(a_empty(as), ((ai / EDGE_NA) & 1) ^ 1u);
         if (profiling) pacc[5] += clock64() - cw0;  // A-ring back-pressure (MMA / weight stream slower than A generation)
+        long long cw1 = profiling ? clock64() : 0;
         tc_fence_after();
         tmem_st8(trow + EDGE_ACOL + as * 32 + qq * 8, w);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(a_full(as));  // one arrival per warp
+        if (profiling) pacc[11] += clock64() - cw1;  // A-operand hand-off (tcgen05.st + wait + publish)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
@@ -933,7 +940,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       if (profiling) { long long c = clock64(); pacc[4] += c - c0; pacc[6] += 1; }  // pass 2 / coordinate update
     }
     if (profiling)
-      for (int k = 0; k < 11; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = pacc[k];
+      for (int k = 0; k < 12; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = pacc[k];
   }
   tc_fence_before();
   __syncthreads();

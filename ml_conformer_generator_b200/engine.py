@@ -217,7 +217,7 @@ class Engine:
         out = (C.c_double * 16)()
         self._check(self.lib.mlcg_edge_phase_profile(self.h, layer, out, self._stream()), "edge_phase_profile")
         names = ["rowinfo_pq_wait", "a_gen", "mma_tail", "pass1", "pass2", "a_ring_backpressure", "tiles",
-                 "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout"]
+                 "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout", "a_handoff"]
         return {n: float(out[i]) for i, n in enumerate(names)}
 
     def test_gemm(self, mode: str, bn: int, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
