@@ -139,11 +139,11 @@ static cudaError_t launch_gemm_mode(int mode, const GemmArgs& a, int n_mtiles, i
   return mode == PREC_BF16 ? launch_gemm<PREC_BF16, BN, kEpi>(a, n_mtiles, n_ntiles, st)
                            : launch_gemm<PREC_TF32, BN, kEpi>(a, n_mtiles, n_ntiles, st);
 }
-template <int kMode, bool kEquiv, bool kPair>
+template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false>
 static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv, kPair, kDistF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          EdgeSmemT<kMode>::ALLOC);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -160,7 +160,7 @@ static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair>, a);
+  return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair, kDistF32>, a);
 }
 // Edge tiles are 128-row ranges of a molecule's edge list that may split a target node's neighbours over two tiles
 // (default); MLCG_EDGE_SPLIT=0 keeps whole targets per tile (lower row occupancy, no fix-up kernel).
@@ -169,6 +169,16 @@ static bool edge_split_mode() {
   if (v < 0) {
     const char* e = getenv("MLCG_EDGE_SPLIT");
     v = (e == nullptr) ? 1 : (atoi(e) != 0);
+  }
+  return v != 0;
+}
+// bf16 mode evaluates the first-layer distance terms d2 * wc + d0^2 * wd in packed bf16x2 (default) or, with
+// MLCG_EDGE_DIST_FP32=1, in fp32 (slower, tighter when the distance terms dominate the pre-activation).
+static bool edge_dist_fp32() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLCG_EDGE_DIST_FP32");
+    v = (e != nullptr) && (atoi(e) != 0);
   }
   return v != 0;
 }
@@ -184,6 +194,11 @@ static bool edge_pair_mode() {
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
+  if (mode == PREC_BF16 && edge_dist_fp32()) {
+    if (pair)
+      return equiv ? launch_edge<PREC_BF16, true, true, true>(a, grid, st) : launch_edge<PREC_BF16, false, true, true>(a, grid, st);
+    return equiv ? launch_edge<PREC_BF16, true, false, true>(a, grid, st) : launch_edge<PREC_BF16, false, false, true>(a, grid, st);
+  }
   if (mode == PREC_BF16) {
     if (pair) return equiv ? launch_edge<PREC_BF16, true, true>(a, grid, st) : launch_edge<PREC_BF16, false, true>(a, grid, st);
     return equiv ? launch_edge<PREC_BF16, true, false>(a, grid, st) : launch_edge<PREC_BF16, false, false>(a, grid, st);

@@ -68,6 +68,42 @@ def test_teacher_forced_trajectory(engines, mode):
     assert worst < TOL[mode]
 
 
+_DIST_FP32_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from conftest import golden, rel_l2
+from ml_conformer_generator_b200.config import CONTEXT_NORMS
+from ml_conformer_generator_b200.engine import Engine
+from ml_conformer_generator_b200.weights import random_state_dicts
+from oracle import edm_oracle as O
+edm_sd, _ = random_state_dicts(0)
+e = Engine(torch.device("cuda:0"), "bf16"); e.load_edm_state_dict(edm_sd)
+g = golden("edm_forward_T10"); B = len(g["n_nodes"])
+e.set_batch(g["n_nodes"], int(g["n_max"]))
+c = O.normalise_context(torch.tensor(np.asarray(g["raw_context"]), dtype=torch.float32), CONTEXT_NORMS).view(1, 3).repeat(B, 1)
+worst = 0.0
+for k in range(g["traj_z"].shape[0]):
+    eps = e.egnn_forward(torch.from_numpy(g["traj_t"][k]).view(-1), torch.from_numpy(g["traj_z"][k]), c)
+    worst = max(worst, rel_l2(eps, g["traj_eps"][k]))
+print("WORST", worst)
+"""
+
+
+def test_teacher_forced_bf16_fp32_distance_terms():
+    """MLCG_EDGE_DIST_FP32=1 (read once per process, hence the subprocess): bf16 mode with the first-layer distance terms
+    in fp32 is tighter on the random-weight trajectory, whose late steps are dominated by d2 * wc."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MLCG_EDGE_DIST_FP32="1")
+    out = subprocess.run([sys.executable, "-c", _DIST_FP32_SCRIPT, root], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float([ln for ln in out.stdout.splitlines() if ln.startswith("WORST")][-1].split()[1])
+    print("teacher-forced worst eps rel-L2 bf16 (fp32 distance terms)", worst)
+    assert worst < 1e-2
+
+
 def _tape(g, B):
     return O.NoiseTape.draw(int(g["n_pairs"]), B, int(g["n_max"]), int(g["seed"])).stacked()
 
