@@ -252,6 +252,11 @@ struct EdgeSmemT {
   static constexpr int BAR_OFF = PROF_OFF + 128;
   static constexpr int TOTAL = BAR_OFF + 256;
   static constexpr int ALLOC = TOTAL + 1024;
+  // bf16 GCL: staging of the tile's messages for the segment-sum MMAs, four 32 KB channel blocks (128 channels x 128 rows,
+  // the last one half used).  Blocks 0,1 live in the scratch area, blocks 2,3 in the W ring, which is idle between the
+  // tile's last main MMA and the next tile's first weight chunk.
+  __host__ __device__ static constexpr int stage_off(int cb) { return cb < 2 ? SCR_OFF + cb * 2 * A_CHUNK_BYTES : W_OFF + (cb - 2) * 2 * A_CHUNK_BYTES; }
+  static_assert(!BF || (2 * 2 * A_CHUNK_BYTES <= EDGE_NW * EDGE_WSLOT), "W ring too small for two staging blocks");
 };
 
 // One 128-row tile of the edge list of a molecule.  The n(n-1) real edges of a molecule are enumerated target-major
@@ -463,6 +468,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             bulk_g2s(base + EdgeSmem::Q_OFF + j * EdgeSmem::PQ_PITCH,
                      pqb + (size_t)(node0 + j) * (2 * EdgeSmem::PQ_ROW) + EdgeSmem::PQ_ROW, EdgeSmem::PQ_ROW, pq_full);
         prev_mol = mol;
+        if constexpr (kSegMma) {
+          // the W ring doubles as staging for the previous tile's messages until its segment-sum MMAs have completed
+          if (it > 0) mbar_wait(e_done(0), (uint32_t)((it - 1) & 1));
+        }
         if constexpr (kPair) {
           // one ring slot per K chunk: this CTA's 112 rows of each N half (2 x 14,336 B)
           for (int kc = 0; kc < p.n_kc; ++kc, ++wi) {
@@ -550,24 +559,22 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // 16r .. 16r+15.
           constexpr uint32_t idesc2 = umma_idesc(1, MM, kPair ? 32 : 16) | (1u << 15);  // A is MN-major
           constexpr int D2W = kPair ? 32 : 16;
+          // all four channel blocks of the tile are staged (pass 1) and the gate-weighted selector is built: one batch
+          mbar_wait(e_full(0), (uint32_t)(it & 1));
+          tc_fence_after();
           for (int cb = 0; cb < 4; ++cb) {
-            const int eb = cb & 1;
-            if constexpr (kPair) mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
-            else mbar_wait(e_full(eb), (uint32_t)((it * 2 + (cb >> 1)) & 1));
-            tc_fence_after();
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t adesc =
-                  umma_desc_mn_sw128(base + EdgeSmem::SCR_OFF + eb * 2 * A_CHUNK_BYTES + ks * 2048, A_CHUNK_BYTES);
-              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (it & 1) * 4096 + (ks >> 2) * 2048) + 2 * (ks & 3);
+              const uint64_t adesc = umma_desc_mn_sw128(base + EdgeSmem::stage_off(cb) + ks * 2048, A_CHUNK_BYTES);
+              const uint64_t bdesc = umma_desc_sw128(base + EdgeSmem::SEL_OFF + (ks >> 2) * 2048) + 2 * (ks & 3);
               // results go to D columns cb*D2W.. : D is free (every warp arrived on e_full only after its pass 1) and the
               // next tile's MMAs cannot start before every warp has finished this tile's readout
               if constexpr (kPair) umma_ss_bf16_pair(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
               else umma<PREC_BF16>(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
             }
-            if constexpr (kPair) umma_commit_pair(e_done(eb), 3);
-            else umma_commit(e_done(eb));
           }
+          if constexpr (kPair) umma_commit_pair(e_done(0), 3);
+          else umma_commit(e_done(0));
         }
       }
     }
@@ -610,23 +617,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           const float inv = 1.0f / sqrtf(d2 + 1e-8f);
           float* tr = trs_all + buf * TILE_M * 3 + rr * 3;
           tr[0] = dx * inv; tr[1] = dy * inv; tr[2] = dz * inv;
-        }
-      }
-      if constexpr (kSegMma) {
-        // S[g][k] = 1 if tile row k belongs to target node g: thread = (group g, 16-byte piece of 8 rows)
-        if (ct >= 256) {
-          const int g = (ct - 256) >> 4, piece = ct & 15;
-          const int lo_k = max(g * nm1 - off0, 0), hi_k = min((g + 1) * nm1 - off0, nrows);  // rows of group g (may be empty)
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int k = piece * 8 + 2 * e;
-            const uint32_t lo = (k >= lo_k && k < hi_k) ? 0x3f80u : 0u;          // bf16 1.0
-            const uint32_t hi = (k + 1 >= lo_k && k + 1 < hi_k) ? 0x3f80u : 0u;
-            w[e] = lo | (hi << 16);
-          }
-          *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + buf * 4096 + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
-              make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     };
@@ -741,7 +731,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       float dotp[4] = {0.f, 0.f, 0.f, 0.f};
       // thread (row r, quarter qq) owns output columns 112*qq .. 112*qq+111 in 7 runs of 16.  GCL bf16 mode keeps the
       // SiLU'd messages as packed bf16 in registers (ew) for pass 2; the other variants write them back to TMEM.
-      uint32_t ew[kSegMma ? 56 : 1];
       // software-pipelined TMEM reads: the load of run ch+1 is in flight while run ch is processed
       float vbuf[2][16];
       tmem_ld16(trow + qq * 112, vbuf[0]);
@@ -751,6 +740,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         const int col0 = qq * 112 + ch * 16;  // warp-uniform
         float* v = vbuf[ch & 1];
         if (ch + 1 < 7) tmem_ld16(trow + col0 + 16, vbuf[(ch + 1) & 1]);
+        [[maybe_unused]] uint32_t mw[8];  // the run's 16 messages, packed bf16
         if constexpr (kFast) {
           // packed path: h (fp32, already halved) -> bf16x2, one MUFU.TANH per pair, m = h + h*tanh(h) as HFMA2; the dot
           // with the gate / coordinate vector accumulates the widened halves in fp32
@@ -769,8 +759,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             dotp[2] = fmaf(__uint_as_float(m2b << 16), w4.z, dotp[2]);
             dotp[3] = fmaf(__uint_as_float(m2b & 0xffff0000u), w4.w, dotp[3]);
             if constexpr (kSegMma) {
-              ew[ch * 8 + (e >> 1)] = m2a;
-              ew[ch * 8 + (e >> 1) + 1] = m2b;
+              mw[(e >> 1)] = m2a;
+              mw[(e >> 1) + 1] = m2b;
             }
           }
         } else {
@@ -784,7 +774,21 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           }
         }
         if constexpr (kSegMma) {
-          // messages are already cached in ew (packed bf16)
+          // Stage the (ungated) messages for the segment-sum MMAs -- the gate goes into the selector.  Block cb < 3 holds
+          // runs 2cb, 2cb+1 of every quarter (32 channels x 4 quarters = 128 MMA rows, row m = 32*qq + c); block 3 holds
+          // run 6 of every quarter (16 channels x 4 = 64 rows, m = 16*qq + c).  Layout per block: two 16 KB operand
+          // chunks of [128 tile rows x 64 channels], i.e. MN-major A with M = channels, K = tile rows.
+          uint8_t* dst;
+          int piece;
+          if (ch < 6) {
+            dst = gbase + EdgeSmem::stage_off(ch >> 1) + (qq >> 1) * A_CHUNK_BYTES;
+            piece = (qq & 1) * 4 + (ch & 1) * 2;
+          } else {
+            dst = gbase + EdgeSmem::stage_off(3);
+            piece = qq * 2;
+          }
+          *reinterpret_cast<uint4*>(dst + sw128_offset(r, piece)) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+          *reinterpret_cast<uint4*>(dst + sw128_offset(r, piece + 1)) = make_uint4(mw[4], mw[5], mw[6], mw[7]);
         } else if constexpr (!kEquiv) {
           tmem_st16(trow + col0, v);
         }
@@ -824,13 +828,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         // e_ij = m_ij * sigmoid(w_a.m_ij + b_a); agg_i = sum_j e_ij / 100   (reference egnn.py:48-51, 59-64)
         const float gate = valid ? sigmoid_acc(full_dot + p.att_bias) : 0.f;
         if constexpr (kSegMma) {
-          // Staging blocks: block cb < 3 = runs 2cb, 2cb+1 of every quarter (32 channels x 4 quarters = 128 MMA rows,
-          // row m = 32*qq + c); block 3 = run 6 of every quarter (16 channels x 4 = 64 rows, m = 16*qq + c).
-          uint32_t g2;
-          {
-            const uint32_t gb = pack_bf16x2(gate, gate);
-            g2 = gb;
-          }
+          // The messages were staged in pass 1; the gate enters through the selector:
+          //   agg[g][c] = sum_k S'[g][k] * m[k][c],   S'[g][k] = gate_k if tile row k belongs to target g, else 0.
+          long long s0 = profiling ? clock64() : 0;
+          float* gates = trs_all;  // [128]; the coordinate-message buffer is unused by GCL layers
+          if (qq == 0) gates[r] = gate;
           // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
           auto readout = [&](int cb) {
             float v[16];
@@ -859,47 +861,30 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             }
             tc_fence_before();
           };
-          long long s0 = profiling ? clock64() : 0;
-          // Round cb stages block cb into staging buffer cb&1; before reusing a buffer wait for the MMA of round cb-2.
-          // The four results stay in TMEM and are read out together at the end.
+          named_bar_sync(1, EDGE_CT);  // all gates written; every thread's pass-1 staging stores are issued
+          if (ct >= 256) {
+            // thread = (group g, 16-byte piece of 8 tile rows) of the K-major selector [16 groups x 128 rows]
+            const int g = (ct - 256) >> 4, piece = ct & 15;
+            const int lo_k = glo(g), hi_k = ghi(g);  // empty for g >= ng
+            uint32_t w[4];
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            const int eb = cb & 1;
-            if (cb >= 2) {
-              mbar_wait(e_done(eb), (uint32_t)((it * 2 + ((cb - 2) >> 1)) & 1));
-              if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }  // wait for the segment-sum MMA
+            for (int e = 0; e < 4; ++e) {
+              const int k = piece * 8 + 2 * e;
+              const float g0 = (k >= lo_k && k < hi_k) ? gates[k] : 0.f;
+              const float g1 = (k + 1 >= lo_k && k + 1 < hi_k) ? gates[k + 1] : 0.f;
+              w[e] = pack_bf16x2(g0, g1);
             }
-            uint8_t* sbuf = scratch + eb * 2 * A_CHUNK_BYTES;
-            if (cb < 3) {
-              uint8_t* dst = sbuf + (qq >> 1) * A_CHUNK_BYTES;
-#pragma unroll
-              for (int pi = 0; pi < 4; ++pi) {
-                uint32_t o[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o[i]) : "r"(ew[cb * 16 + pi * 4 + i]), "r"(g2));
-                *reinterpret_cast<uint4*>(dst + sw128_offset(r, (qq & 1) * 4 + pi)) = make_uint4(o[0], o[1], o[2], o[3]);
-              }
-            } else {
-#pragma unroll
-              for (int pi = 0; pi < 2; ++pi) {
-                uint32_t o[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(o[i]) : "r"(ew[48 + pi * 4 + i]), "r"(g2));
-                *reinterpret_cast<uint4*>(sbuf + sw128_offset(r, qq * 2 + pi)) = make_uint4(o[0], o[1], o[2], o[3]);
-              }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) arrive_leader(e_full(eb));
-            if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate + stage + fence + arrive
+            *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
+                make_uint4(w[0], w[1], w[2], w[3]);
           }
-          mbar_wait(e_done(0), (uint32_t)((it * 2 + 1) & 1));
-          mbar_wait(e_done(1), (uint32_t)((it * 2 + 1) & 1));
+          fence_proxy_async();  // staging + selector stores -> visible to the tensor core
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(e_full(0));
+          if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate exchange + selector + publish
+          mbar_wait(e_done(0), (uint32_t)(it & 1));
           tc_fence_after();
-          if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }
+          if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }   // segment-sum MMAs
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) readout(cb);
           if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
