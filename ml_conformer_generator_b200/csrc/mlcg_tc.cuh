@@ -224,6 +224,10 @@ constexpr int EDGE_WSLOT = 224 * CHUNK_BYTES;  // 28,672 B: one (K chunk, N half
 constexpr int EDGE_NW = 3;             // W ring slots
 constexpr int EDGE_NWMAX = EDGE_NW;
 constexpr int EDGE_NA = 2;             // A ring stages (TMEM columns 448..479 and 480..511)
+#ifndef MLCG_EDGE_EARLY
+#define MLCG_EDGE_EARLY 2
+#endif
+constexpr int EDGE_EARLY = MLCG_EDGE_EARLY;  // K chunks of the next tile generated during the segment-sum MMAs (bf16 GCL), <= EDGE_NA
 constexpr int EDGE_ACOL = 448;         // first TMEM column of the A ring
 constexpr int EDGE_QPITCH = 452;       // floats; 1808 B rows -> conflict-free LDS.128 across consecutive j
 constexpr int EDGE_CT = 512;           // compute threads (16 warps)
@@ -643,12 +647,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       const uint8_t* Prow = Ps + (info & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;  // invalid rows read row 0
       const uint8_t* Qrow = Qs + ((info >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
       const uint32_t d2h = pack_bf16x2(rd.x, rd.x), d02h = pack_bf16x2(rd.y, rd.y);  // bf16 mode: packed distance features
-      mbar_wait(pq_full, (uint32_t)(it & 1));
+      if (!(kSegMma && it > 0)) mbar_wait(pq_full, (uint32_t)(it & 1));  // (bf16 GCL: waited for during the previous tile)
       if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
-      // ---- A generation: SiLU(P_i + Q_j + d2*wc + d02*wd) -> TMEM A ring ----
-#pragma unroll 1
-      for (int kc = 0; kc < p.n_kc; ++kc, ++ai) {
+      // One K chunk of the A operand for the tile whose row data is (Prow, Qrow, rd, d2h, d02h): SiLU(P_i + Q_j + d2*wc +
+      // d02*wd) -> TMEM A ring stage ai % 2.
+      auto agen_chunk = [&](int kc, const uint8_t* Prow, const uint8_t* Qrow, float2 rd, uint32_t d2h, uint32_t d02h) {
         const int as = ai % EDGE_NA;
         const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
         uint32_t w[8];
@@ -718,6 +722,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         __syncwarp();
         if (lane == 0) arrive_leader(a_full(as));  // one arrival per warp
         if (profiling) pacc[11] += clock64() - cw1;  // A-operand hand-off (tcgen05.st + wait + publish)
+        ++ai;
+      };
+      // ---- A generation ----  (bf16 GCL: chunks 0 and 1 were generated during the previous tile's segment-sum MMAs)
+      {
+        const int kc_begin = (kSegMma && it > 0) ? min(EDGE_EARLY, p.n_kc) : 0;
+#pragma unroll 1
+        for (int kc = kc_begin; kc < p.n_kc; ++kc) agen_chunk(kc, Prow, Qrow, rd, d2h, d02h);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(pq_empty);  // P/Q rows of this tile are no longer needed
@@ -793,11 +804,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           tmem_st16(trow + col0, v);
         }
         if (ch + 1 < 7) tmem_wait_ld();
-      }
-      if constexpr (kSegMma) {  // D has been fully consumed: the next tile's MMAs may overwrite it
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_leader(d_empty);
       }
       dots[qq * TILE_M + r] = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
       if constexpr (!kEquiv && !kSegMma) tmem_wait_st();
@@ -882,11 +888,27 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           __syncwarp();
           if (lane == 0) arrive_leader(e_full(0));
           if (profiling) { long long c = clock64(); pacc[9] += c - s0; s0 = c; }   // gate exchange + selector + publish
+          // While the tensor core runs the segment-sum MMAs the MUFU pipe is idle and the A ring is free: generate the
+          // first two K chunks of the NEXT tile now.  Its MMAs cannot start before this tile's readout (they wait for
+          // d_empty, which is released after the readout), but then they find both ring stages full.
+          if (it + 1 < n_iter) {
+            const int nb = buf ^ 1;  // row data of tile it+1 (tile_setup ran during this tile's MMA tail)
+            const int info2 = ri_gj_all[nb * TILE_M + r];
+            const float2 rd2 = ri_d_all[nb * TILE_M + r];
+            const uint8_t* Prow2 = Ps + (info2 & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
+            const uint8_t* Qrow2 = Qs + ((info2 >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
+            mbar_wait(pq_full, (uint32_t)((it + 1) & 1));
+            for (int kc = 0; kc < min(EDGE_EARLY, p.n_kc); ++kc)
+              agen_chunk(kc, Prow2, Qrow2, rd2, pack_bf16x2(rd2.x, rd2.x), pack_bf16x2(rd2.y, rd2.y));
+          }
           mbar_wait(e_done(0), (uint32_t)(it & 1));
           tc_fence_after();
           if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }   // segment-sum MMAs
 #pragma unroll
           for (int cb = 0; cb < 4; ++cb) readout(cb);
+          // D (which held the segment sums) is free: the next tile's MMAs may start
+          __syncwarp();
+          if (lane == 0) arrive_leader(d_empty);
           if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
         } else {
 #pragma unroll 1
@@ -930,7 +952,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           }
         }
         }
-        named_bar_sync(1, EDGE_CT);  // staging is free again
+        if constexpr (!kSegMma) named_bar_sync(1, EDGE_CT);  // staging is free again (bf16 GCL: next written after later barriers)
       }
       if (profiling) { long long c = clock64(); pacc[4] += c - c0; pacc[6] += 1; }  // pass 2 / coordinate update
     }
