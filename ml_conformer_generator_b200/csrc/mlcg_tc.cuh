@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   constexpr int EPC = epc(kMode);
   constexpr int ELEMS = EPC / 4;  // K elements per thread per chunk (16 bf16 / 8 tf32) = 8 TMEM columns
   constexpr bool kSegMma = (kMode == PREC_BF16) && !kEquiv;  // neighbour sum on the tensor core (bf16 mode)
+  constexpr bool kEarlyA = (kMode == PREC_BF16);  // first A chunks of tile t+1 are generated inside the epilogue of tile t
   using EdgeSmem = EdgeSmemT<kMode>;
   constexpr bool kPqBf16 = EdgeSmem::BF;
   extern __shared__ uint8_t smem_raw[];
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       const uint8_t* Prow = Ps + (info & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;  // invalid rows read row 0
       const uint8_t* Qrow = Qs + ((info >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
       const uint32_t d2h = pack_bf16x2(rd.x, rd.x), d02h = pack_bf16x2(rd.y, rd.y);  // bf16 mode: packed distance features
-      if (!(kSegMma && it > 0)) mbar_wait(pq_full, (uint32_t)(it & 1));  // (bf16 GCL: waited for during the previous tile)
+      if (!(kEarlyA && it > 0)) mbar_wait(pq_full, (uint32_t)(it & 1));  // (bf16: waited for during the previous tile)
       if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
       // One K chunk of the A operand for the tile whose row data is (Prow, Qrow, rd, d2h, d02h): SiLU(P_i + Q_j + d2*wc +
@@ -724,9 +725,23 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         if (profiling) pacc[11] += clock64() - cw1;  // A-operand hand-off (tcgen05.st + wait + publish)
         ++ai;
       };
-      // ---- A generation ----  (bf16 GCL: chunks 0 and 1 were generated during the previous tile's segment-sum MMAs)
+      // First EDGE_EARLY chunks of tile it+1 (row data from the other metadata buffer: tile_setup ran during this tile's
+      // MMA tail).  Called inside the epilogue of tile it, when the MUFU pipe is idle and the A ring is free.
+      auto agen_early = [&]() {
+        if (it + 1 < n_iter) {
+          const int nb = buf ^ 1;
+          const int info2 = ri_gj_all[nb * TILE_M + r];
+          const float2 rd2 = ri_d_all[nb * TILE_M + r];
+          const uint8_t* Prow2 = Ps + (info2 & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
+          const uint8_t* Qrow2 = Qs + ((info2 >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
+          mbar_wait(pq_full, (uint32_t)((it + 1) & 1));
+          for (int kc = 0; kc < min(EDGE_EARLY, p.n_kc); ++kc)
+            agen_chunk(kc, Prow2, Qrow2, rd2, pack_bf16x2(rd2.x, rd2.x), pack_bf16x2(rd2.y, rd2.y));
+        }
+      };
+      // ---- A generation ----  (bf16: chunks 0 and 1 were generated during the previous tile's epilogue)
       {
-        const int kc_begin = (kSegMma && it > 0) ? min(EDGE_EARLY, p.n_kc) : 0;
+        const int kc_begin = (kEarlyA && it > 0) ? min(EDGE_EARLY, p.n_kc) : 0;
 #pragma unroll 1
         for (int kc = kc_begin; kc < p.n_kc; ++kc) agen_chunk(kc, Prow, Qrow, rd, d2h, d02h);
       }
@@ -829,6 +844,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
           else p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
         }
+        if constexpr (kEarlyA) agen_early();  // D was released above: the next tile's MMAs start as soon as chunk 0 is published
         named_bar_sync(1, EDGE_CT);
       } else {
         // e_ij = m_ij * sigmoid(w_a.m_ij + b_a); agg_i = sum_j e_ij / 100   (reference egnn.py:48-51, 59-64)
@@ -891,16 +907,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // While the tensor core runs the segment-sum MMAs the MUFU pipe is idle and the A ring is free: generate the
           // first two K chunks of the NEXT tile now.  Its MMAs cannot start before this tile's readout (they wait for
           // d_empty, which is released after the readout), but then they find both ring stages full.
-          if (it + 1 < n_iter) {
-            const int nb = buf ^ 1;  // row data of tile it+1 (tile_setup ran during this tile's MMA tail)
-            const int info2 = ri_gj_all[nb * TILE_M + r];
-            const float2 rd2 = ri_d_all[nb * TILE_M + r];
-            const uint8_t* Prow2 = Ps + (info2 & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
-            const uint8_t* Qrow2 = Qs + ((info2 >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
-            mbar_wait(pq_full, (uint32_t)((it + 1) & 1));
-            for (int kc = 0; kc < min(EDGE_EARLY, p.n_kc); ++kc)
-              agen_chunk(kc, Prow2, Qrow2, rd2, pack_bf16x2(rd2.x, rd2.x), pack_bf16x2(rd2.y, rd2.y));
-          }
+          agen_early();
           mbar_wait(e_done(0), (uint32_t)(it & 1));
           tc_fence_after();
           if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }   // segment-sum MMAs
