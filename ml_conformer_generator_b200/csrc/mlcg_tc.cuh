@@ -127,16 +127,16 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
     mbar_wait(dfull_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float rs = 1.0f;
-    if (kEpi == EPI_F32 && p.rowscale != nullptr && rvalid) rs = p.rowscale[grow];
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(trow + c0, v);
-      tmem_wait_ld();
-      const int gcol = nt * BN + c0;
-      if (rvalid) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
-        if constexpr (kEpi == EPI_F32) {
+    if constexpr (kEpi == EPI_F32) {
+      float rs = 1.0f;
+      if (p.rowscale != nullptr && rvalid) rs = p.rowscale[grow];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_wait_ld();
+        const int gcol = nt * BN + c0;
+        if (rvalid) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
           float* orow = p.out_f32 + (size_t)grow * p.ldo + gcol;
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
@@ -157,42 +157,100 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
               if (gcol + e + 2 < p.n_valid) orow[e + 2] = o.z;
             }
           }
-        } else if constexpr (kEpi == EPI_BF16) {
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out_f32) + (size_t)grow * p.ldo + gcol;
+        }
+      }
+    } else {
+      // The accumulator is read with thread = row, but a warp-wide 16-byte store with thread = row touches 32 different
+      // 128-byte lines.  Every 128-byte-per-row block therefore goes through a warp-private staging buffer (32 rows x
+      // 128 B, 16-byte pieces XOR-swizzled by row & 7 = exactly the operand-format image of these rows) and is moved to /
+      // from global memory with lane = (row 4i + lane/8, piece lane%8): 4 full 128-byte lines per instruction.  The
+      // staging lives in the first ring stage, which is idle once the last MMA has completed.
+      constexpr int EPC = epc(kMode);
+      uint8_t* stg = gen_base + q * 4096;
+      const int crow = lane >> 3, cpiece = lane & 7;
+      auto stg_at = [&](int r, int pc) { return stg + r * 128 + ((pc ^ (r & 7)) << 4); };
+      const int row0 = mt * TILE_M + q * 32;  // first global row of this warp
+      uint32_t ow[32];                        // packed words of the current 128-byte output block (thread's row)
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + c0, v);
+        tmem_wait_ld();
+        const int gcol = nt * BN + c0;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
+        if constexpr (kEpi == EPI_RESID_OP) {
+          // residual block of the warp: 32 rows x 32 floats, contiguous 4 KB in the tiled layout
+          float* rblk = p.resid + hres_index(row0, gcol, 0);
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            const float4 b0 = __ldg(b4 + (e >> 2)), b1 = __ldg(b4 + (e >> 2) + 1);
-            uint4 o;
-            o.x = pack_bf16x2(v[e + 0] + b0.x, v[e + 1] + b0.y);
-            o.y = pack_bf16x2(v[e + 2] + b0.z, v[e + 3] + b0.w);
-            o.z = pack_bf16x2(v[e + 4] + b1.x, v[e + 5] + b1.y);
-            o.w = pack_bf16x2(v[e + 6] + b1.z, v[e + 7] + b1.w);
-            *reinterpret_cast<uint4*>(orow + e) = o;
-          }
-        } else if constexpr (kEpi == EPI_SILU_OP) {
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(stg_at(4 * i + crow, cpiece)) = reinterpret_cast<const uint4*>(rblk)[i * 32 + lane];
+          __syncwarp();
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 b = __ldg(b4 + (e >> 2));
-            v[e + 0] = silu<kFast>(v[e + 0] + b.x);
-            v[e + 1] = silu<kFast>(v[e + 1] + b.y);
-            v[e + 2] = silu<kFast>(v[e + 2] + b.z);
-            v[e + 3] = silu<kFast>(v[e + 3] + b.w);
-          }
-          op_store<kMode, 32>(p.out_op, p.out_op_chunks, grow, gcol, v);
-        } else {
-          float* rrow = p.resid + hres_index(grow, gcol, p.ldr);  // 32 consecutive floats in both layouts
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 b = __ldg(b4 + (e >> 2));
-            float4 h = *reinterpret_cast<const float4*>(rrow + e);
+            float4 h = *reinterpret_cast<const float4*>(stg_at(lane, e >> 2));
             h.x += v[e + 0] + b.x;
             h.y += v[e + 1] + b.y;
             h.z += v[e + 2] + b.z;
             h.w += v[e + 3] + b.w;
-            *reinterpret_cast<float4*>(rrow + e) = h;
+            *reinterpret_cast<float4*>(stg_at(lane, e >> 2)) = h;
             v[e + 0] = h.x; v[e + 1] = h.y; v[e + 2] = h.z; v[e + 3] = h.w;
           }
-          op_store<kMode, 32>(p.out_op, p.out_op_chunks, grow, gcol, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (row0 + 4 * i + crow < p.m_rows)
+              reinterpret_cast<uint4*>(rblk)[i * 32 + lane] = *reinterpret_cast<const uint4*>(stg_at(4 * i + crow, cpiece));
+          __syncwarp();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b = __ldg(b4 + (e >> 2));
+            if constexpr (kEpi == EPI_SILU_OP) {
+              v[e + 0] = silu<kFast>(v[e + 0] + b.x); v[e + 1] = silu<kFast>(v[e + 1] + b.y);
+              v[e + 2] = silu<kFast>(v[e + 2] + b.z); v[e + 3] = silu<kFast>(v[e + 3] + b.w);
+            } else {
+              v[e + 0] += b.x; v[e + 1] += b.y; v[e + 2] += b.z; v[e + 3] += b.w;
+            }
+          }
+        }
+        // pack into the 128-byte output block of this row
+        const bool flush = (EPC == 32) || ((c0 & 32) != 0);
+        if constexpr (EPC == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ow[j] = f32_to_tf32(v[j]);
+        } else {
+          if ((c0 & 32) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ow[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ow[16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          }
+        }
+        if (flush) {
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc)
+            *reinterpret_cast<uint4*>(stg_at(lane, pc)) = make_uint4(ow[4 * pc], ow[4 * pc + 1], ow[4 * pc + 2], ow[4 * pc + 3]);
+          __syncwarp();
+          const int cb0 = nt * BN + (c0 / EPC) * EPC;  // first channel of the block
+          if constexpr (kEpi == EPI_BF16) {
+            // row-major bf16 rows of ldo elements
+            uint8_t* obase = reinterpret_cast<uint8_t*>(p.out_f32) + (size_t)cb0 * 2 + cpiece * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + crow;
+              if (row0 + r < p.m_rows)
+                *reinterpret_cast<uint4*>(obase + (size_t)(row0 + r) * p.ldo * 2) = *reinterpret_cast<const uint4*>(stg_at(r, cpiece));
+            }
+          } else {
+            // operand format: the staging image is the destination image (same swizzle): linear 4 KB copy
+            uint8_t* dst = p.out_op + ((size_t)mt * p.out_op_chunks + cb0 / EPC) * A_CHUNK_BYTES + q * 4096;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (row0 + 4 * i + crow < p.m_rows)
+                reinterpret_cast<uint4*>(dst)[i * 32 + lane] = reinterpret_cast<const uint4*>(stg)[i * 32 + lane];
+          }
+          __syncwarp();
         }
       }
     }
