@@ -173,6 +173,14 @@ class MLConformerGenerator:
         return {"x": x, "atom_class": cls, "n_nodes": n_nodes, "elements": el, "dist_mat": dist, "adj_mat": adj,
                 "bond_logits": logits, "bonds": bonds}
 
+    def generate_sdf(self, reference_context: torch.Tensor, n_atoms: int, n_samples: int = 10, variance: int = 2,
+                     resample_steps: int = 0, **fragment_kwargs) -> List[str]:
+        """generate_tensors + an RDKit-free V2000 writer: one mol block per sample with the GCN's bond orders.  No
+        sanitisation / hydrogens / MMFF (those are RDKit's, reference conformer_generator.py:357-368)."""
+        from .mol_utils import samples_to_sdf_blocks
+        t = self.generate_tensors(reference_context, n_atoms, n_samples, variance, resample_steps, **fragment_kwargs)
+        return samples_to_sdf_blocks(t["x"], t["atom_class"], t["bonds"], t["n_nodes"])
+
     # ------------------------------------------------------------------------------------------------------------
     # RDKit-facing path, same signatures as the reference
     # ------------------------------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ Mirrors the *tensor half* of the reference's `src/mlconfgen/utils/mol_utils.py` 
 behaviour; file:line cited per function).  Everything that needs RDKit stays in the reference (SURVEY.md section 2,
 rows 6-8); a fixed-column V2000 reader is provided so contexts / fragments can be taken from `.mol` files without it.
 """
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -229,6 +229,54 @@ def samples_to_xyz_blocks(x: torch.Tensor, atom_class: torch.Tensor, n_nodes: to
         rows = ["%s %.9f %.9f %.9f" % (ATOM_DECODER[int(cls[b, i])], x[b, i, 0], x[b, i, 1], x[b, i, 2]) for i in range(n)]
         out.append("%d\n\n%s\n" % (n, "\n".join(rows)))
     return out
+
+
+def bond_orders_from_logits(logits: torch.Tensor) -> torch.Tensor:
+    """(B,42,42,5) AdjMatSeer logits -> (B,42,42) bond order 0..4 for i > j (lower triangle, zero diagonal), as the
+    reference's redefine_bonds does per molecule (mol_utils.py:210-211)."""
+    order = torch.argmax(logits, dim=-1)
+    return torch.tril(order, diagonal=-1)
+
+
+def samples_to_sdf_blocks(x: torch.Tensor, atom_class: torch.Tensor, bonds: torch.Tensor, n_nodes: torch.Tensor,
+                          names: Optional[Sequence[str]] = None) -> List[str]:
+    """V2000 mol blocks ("...M  END\n$$$$\n") from the accelerated path's tensors, without RDKit.
+
+    x (B,N,3) coordinates, atom_class (B,N) (-1 = padding), bonds (B,D,D) bond order per pair as mlcg_seer_forward /
+    bond_orders_from_logits return it (only i > j is read; 1 single, 2 double, 3 triple, 4 aromatic -- the reference's
+    bond_type_dict, mol_utils.py:10-15).  This is the wire format of the reference's results (Chem.MolToMolBlock in
+    cheminformatics/pipeline.py:88) minus RDKit's sanitisation: no implicit hydrogens, no charge / valence fix-up."""
+    x = x.detach().cpu()
+    cls = atom_class.detach().cpu()
+    bo = bonds.detach().cpu()
+    out = []
+    for b in range(x.size(0)):
+        n = int(n_nodes[b])
+        if n > 999:
+            raise ValueError("V2000 mol blocks hold at most 999 atoms")
+        pairs = [(i, j, int(bo[b, i, j])) for i in range(n) for j in range(i) if int(bo[b, i, j]) != 0]
+        lines = [names[b] if names is not None else "mlcg_%d" % b, "  ml_conformer_generator_b200", "",
+                 "%3d%3d  0  0  0  0  0  0  0  0999 V2000" % (n, len(pairs))]
+        for i in range(n):
+            lines.append("%10.4f%10.4f%10.4f %-3s 0  0  0  0  0  0  0  0  0  0  0  0"
+                         % (float(x[b, i, 0]), float(x[b, i, 1]), float(x[b, i, 2]), ATOM_DECODER[int(cls[b, i])]))
+        for i, j, order in pairs:
+            lines.append("%3d%3d%3d  0" % (j + 1, i + 1, order))
+        lines += ["M  END", "$$$$"]
+        out.append("\n".join(lines) + "\n")
+    return out
+
+
+def read_mol_block(block: str) -> Tuple[List[str], torch.Tensor, List[Tuple[int, int, int]]]:
+    """Inverse of samples_to_sdf_blocks for one V2000 block: symbols, coordinates (n,3), bonds [(a, b, order)] with
+    0-based atom indices."""
+    lines = block.splitlines()
+    n_atoms, n_bonds = int(lines[3][0:3]), int(lines[3][3:6])
+    symbols = [ln[31:34].strip() for ln in lines[4:4 + n_atoms]]
+    xyz = torch.tensor([[float(ln[0:10]), float(ln[10:20]), float(ln[20:30])] for ln in lines[4:4 + n_atoms]],
+                       dtype=torch.float32).view(-1, 3)
+    bonds = [(int(ln[0:3]) - 1, int(ln[3:6]) - 1, int(ln[6:9])) for ln in lines[4 + n_atoms:4 + n_atoms + n_bonds]]
+    return symbols, xyz, bonds
 
 
 def atomic_numbers(atom_class: torch.Tensor) -> torch.Tensor:

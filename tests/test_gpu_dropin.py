@@ -97,3 +97,17 @@ def test_generate_tensors_modes(generators):
         cls = out["atom_class"].cpu()
         for b in range(6):
             assert bool((cls[b, : n[b]] >= 0).all()) and bool((cls[b, n[b]:] == -1).all())
+
+
+def test_generate_sdf(generators):
+    """generate_sdf: the accelerated path straight to V2000 blocks (no RDKit); blocks parse back to consistent molecules."""
+    from ml_conformer_generator_b200.mol_utils import read_mol_block
+    gen = generators(4, "bf16")
+    ctx = torch.from_numpy(golden("host_utils")["ceyyag_context"])
+    blocks = gen.generate_sdf(ctx, n_atoms=17, n_samples=5, variance=2)
+    assert len(blocks) == 5
+    for blk in blocks:
+        sym, xyz, bonds = read_mol_block(blk)
+        assert 15 <= len(sym) <= 19 and xyz.shape == (len(sym), 3) and torch.isfinite(xyz).all()
+        assert all(s in ("C", "N", "O", "F", "P", "S", "Cl", "Br") for s in sym)
+        assert all(0 <= a < b < len(sym) and 1 <= o <= 4 for a, b, o in bonds)
