@@ -144,6 +144,30 @@ int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, con
                   uint64_t seed, int64_t sample_offset, float* x_host, int32_t* atom_class_host, int8_t* bonds_host,
                   void* stream);
 
+/* ---- Gaussian shape similarity (the tensor part of the reference's evaluate_samples) -------------------------------
+ * Replaces get_shape_quadrupole_for_molecule (cheminformatics/shape_similarity.py:18-203: clique enumeration :267-311 and
+ * the inclusion-exclusion moment series) up to the 3x3 eigen-decomposition, which stays on the host (torch.linalg.eigh,
+ * as the reference, :139), and tanimoto_score / rotate_coord (:422-492) for all samples and orientations at once.
+ * These entry points use the handle only for its device and error slot; no weights or batch plan are needed. */
+
+/* coords (B,N,3) fp32 device, n_nodes (B) int32 device, 1 <= n_nodes[b] <= 64.  out (B,16) fp32 device:
+ * [0] Gaussian volume, [1..3] first moments (relative to the atom mean), [4..12] second-moment tensor about the first
+ * moment divided by the volume (row-major 3x3; s_mom_tensor_0 of :126-135), [13..15] atom mean.
+ * amplitude / atom_radius / n_terms: the reference's AMPLITUDE 2.70, ATOM_RADIUS 1.60, 6. */
+int mlcg_shape_moments(mlcg_handle* h, const float* coords, const int32_t* n_nodes, int B, int N, float amplitude,
+                       float atom_radius, int n_terms, float* out, void* stream);
+
+/* Grid Tanimoto of every (sample, orientation) against a reference molecule.
+ * ref_pts (n_ref,3): reference atoms in their principal frame; coords (B,N,3), n_nodes (B): raw sample coordinates;
+ * frames (B,12): per sample {shift (3), rotation (3x3 row-major)} so that principal = (x - shift) . rotation;
+ * orient (n_orient,9): orientation matrices applied as principal . O (entry 0 is ignored: the unrotated frame, as
+ * pipeline.py:76); axes (3,G): grid coordinates per axis (Grid of :381-403, built by the caller), G <= 48;
+ * workspace: G^3 + 1 floats (reference density and its squared sum).  Outputs: scores (B,n_orient) =
+ * sum(f g) / (sum f^2 + sum g^2 - sum(f g)); aligned (B,n_orient,N,3) final coordinates, or NULL. All device pointers. */
+int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_ref, const float* coords, const int32_t* n_nodes, int B,
+                        int N, const float* frames, const float* orient, int n_orient, const float* axes, int G,
+                        float amplitude, float atom_radius, float* workspace, float* scores, float* aligned, void* stream);
+
 /* Introspection for benches / tests. */
 int mlcg_num_edge_tiles(mlcg_handle* h);
 int64_t mlcg_num_edges(mlcg_handle* h);          /* sum_b n_b (n_b - 1) */

@@ -10,6 +10,7 @@
 #include "mlcg.h"
 #include "mlcg_kernels.cuh"
 #include "mlcg_tc.cuh"
+#include "mlcg_shape.cuh"
 
 using namespace mlcg;
 
@@ -1165,6 +1166,61 @@ extern "C" int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, v
     for (int k = 0; k < 16; ++k) acc[k] += (double)host[(size_t)b * 16 + k];
   const double tiles = acc[6] > 0 ? acc[6] : 1.0;
   for (int k = 0; k < 16; ++k) out[k] = (k == 6) ? acc[k] : acc[k] / tiles;
+  return MLCG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gaussian shape similarity (reference cheminformatics/shape_similarity.py)
+// ---------------------------------------------------------------------------------------------------------------
+static double shape_alpha(double amplitude, double atom_radius) {  // get_alpha, shape_similarity.py:322-329
+  const double pi = 3.14159265358979323846;
+  const double lam = 4.0 * pi / 3.0 / amplitude;
+  return pi / pow(lam, 2.0 / 3.0) / (atom_radius * atom_radius);
+}
+
+extern "C" int mlcg_shape_moments(mlcg_handle* h, const float* coords, const int32_t* n_nodes, int B, int N, float amplitude,
+                                  float atom_radius, int n_terms, float* out, void* stream) {
+  if (!h) return MLCG_E_ARG;
+  if (!coords || !n_nodes || !out || B <= 0 || N <= 0 || N > SHAPE_MAX_ATOMS || n_terms < 1 || n_terms > SHAPE_MAX_TERMS ||
+      !(amplitude > 0.f) || !(atom_radius > 0.f))
+    FAIL(MLCG_E_ARG, "shape_moments: need B > 0, 1 <= N <= 64, 1 <= n_terms <= 6");
+  CK(cudaSetDevice(h->device));
+  const double pi = 3.14159265358979323846, alpha = shape_alpha(amplitude, atom_radius);
+  ShapeConsts k{};
+  k.amplitude = amplitude;
+  k.alpha = (float)alpha;
+  k.threshold = 2.0f * amplitude;  // neighbour_threshold default, shape_similarity.py:23
+  k.n_terms = n_terms;
+  for (int o = 1; o <= SHAPE_MAX_TERMS; ++o) {
+    k.amp_k[o] = (float)pow((double)amplitude, (double)o);
+    k.vol_k[o] = (float)pow(pi / (o * alpha), 1.5);
+    k.inv2ka[o] = (float)(1.0 / (2.0 * o * alpha));
+  }
+  k_shape_moments<<<B, 128, 0, (cudaStream_t)stream>>>(coords, n_nodes, N, k, out);
+  KCHECK();
+  h->launches++;
+  return MLCG_OK;
+}
+
+extern "C" int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_ref, const float* coords, const int32_t* n_nodes,
+                                   int B, int N, const float* frames, const float* orient, int n_orient, const float* axes,
+                                   int G, float amplitude, float atom_radius, float* workspace, float* scores, float* aligned,
+                                   void* stream) {
+  if (!h) return MLCG_E_ARG;
+  if (!ref_pts || !coords || !n_nodes || !frames || !orient || !axes || !workspace || !scores || B <= 0 || N <= 0 ||
+      N > SHAPE_MAX_ATOMS || n_ref <= 0 || n_ref > SHAPE_MAX_ATOMS || n_orient <= 0 || n_orient > 65535 || G <= 1 ||
+      G > SHAPE_MAX_GRID)
+    FAIL(MLCG_E_ARG, "shape_tanimoto: need 1 <= N, n_ref <= 64, 2 <= G <= 48, n_orient >= 1");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float alpha = (float)shape_alpha(amplitude, atom_radius);
+  k_shape_grid<true><<<dim3(1, 1), 256, 0, st>>>(ref_pts, nullptr, n_ref, n_ref, nullptr, nullptr, 1, axes, G, amplitude, alpha,
+                                                 workspace, nullptr, nullptr);
+  KCHECK();
+  k_shape_grid<false><<<dim3(B, n_orient), 256, 0, st>>>(coords, n_nodes, 0, N, frames, orient, n_orient, axes, G, amplitude,
+                                                         alpha, workspace, scores, aligned);
+  KCHECK();
+  h->launches += 2;
   return MLCG_OK;
 }
 

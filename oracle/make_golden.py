@@ -224,8 +224,61 @@ def host_fixtures():
     save("host_utils", **out)
 
 
+def shape_fixtures():
+    """Golden vectors of the Gaussian shape-similarity path (reference cheminformatics/shape_similarity.py and the tensor
+    part of cheminformatics/pipeline.py:37-86), produced by the reference's own functions."""
+    load_reference()
+    import importlib
+    ss = importlib.import_module("mlconfgen.cheminformatics.shape_similarity")
+    from ml_conformer_generator_b200.mol_utils import read_mol_heavy_atoms
+    demo = "/root/reference/assets/demo_files/"
+    _, ref_xyz = read_mol_heavy_atoms(demo + "ceyyag.mol")
+    _, yib_xyz = read_mol_heavy_atoms(demo + "yibfeu.mol")
+    g = torch.Generator().manual_seed(2024)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    blob = torch.randn(30, 3, generator=g) * 2.0
+    samples = [ref_xyz + 0.3 * torch.randn(ref_xyz.shape, generator=g),
+               (ref_xyz + 0.15 * torch.randn(ref_xyz.shape, generator=g)) @ q + torch.tensor([3.0, -2.0, 1.0]),
+               yib_xyz, blob, ref_xyz[:15].clone()]
+    n_max = max(s.size(0) for s in samples)
+    ref_c = ref_xyz - torch.mean(ref_xyz, dim=0)
+    ref_mom, ref_pts = ss.get_shape_quadrupole_for_molecule(coordinates=ref_c)
+    pi = torch.pi
+    rots = [torch.tensor([pi, 0, 0]), torch.tensor([0, pi, 0]), torch.tensor([0, 0, pi])]
+    B = len(samples)
+    coords = torch.zeros(B, n_max, 3)
+    pts = torch.zeros(B, n_max, 3)
+    best_coord = torch.zeros(B, n_max, 3)
+    moments = torch.zeros(B, 3)
+    scores = torch.zeros(B, 4)
+    best_idx = torch.zeros(B, dtype=torch.long)
+    n_nodes = torch.tensor([s.size(0) for s in samples])
+    for b, xyz in enumerate(samples):
+        n = xyz.size(0)
+        coords[b, :n] = xyz
+        c = xyz - torch.mean(xyz, dim=0)
+        mom, sq = ss.get_shape_quadrupole_for_molecule(coordinates=c)
+        moments[b], pts[b, :n] = mom, sq
+        best, bc = ss.tanimoto_score(ref_pts, sq), sq
+        scores[b, 0] = best
+        for k, ang in enumerate(rots):
+            rc = ss.rotate_coord(coord=sq, angles=ang)
+            sc = ss.tanimoto_score(ref_pts, rc)
+            scores[b, k + 1] = sc
+            if sc > best:
+                best, bc, best_idx[b] = sc, rc, k + 1
+        best_coord[b, :n] = bc
+        print("shape sample", b, n, "scores", scores[b].tolist(), "best", int(best_idx[b]))
+    save("shape", ref_xyz=ref_xyz, ref_moments=ref_mom, ref_pts=ref_pts, coords=coords, n_nodes=n_nodes, moments=moments,
+         pts=pts, scores=scores, best_idx=best_idx, best_coord=best_coord)
+
+
 if __name__ == "__main__":
     import sys
+    if "--shape-only" in sys.argv:
+        shape_fixtures()
+        sys.exit(0)
     if "--host-only" not in sys.argv:
         main()
     host_fixtures()
+    shape_fixtures()

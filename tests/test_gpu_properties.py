@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import rel_l2
+from conftest import golden, rel_l2
 from ml_conformer_generator_b200.config import CONTEXT_NORMS
 from oracle import edm_oracle as O
 
@@ -99,3 +99,54 @@ def test_full_size_generation_properties(engines):
     assert torch.isfinite(a[0]).all() and int(a[1].min()) >= 0 and int(a[1].max()) <= 6
     assert int(a[2].min()) >= 0 and int(a[2].max()) <= 4 and bool((torch.triu(a[2].long()) == 0).all())
     assert float(a[0].mean(dim=1).abs().max()) < 0.5 * float(a[0].abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Gaussian shape similarity against the reference's own outputs (tests/golden/shape.npz)
+# ---------------------------------------------------------------------------------------------------------------
+def _scorer(engines):
+    from ml_conformer_generator_b200.shape_similarity import ShapeScorer
+    return ShapeScorer(engines("bf16"))
+
+
+def test_shape_principal_frames_golden(engines):
+    g = golden("shape")
+    sc = _scorer(engines)
+    ref = torch.from_numpy(g["ref_xyz"])
+    rf = sc.principal_frames(ref.unsqueeze(0), torch.tensor([ref.size(0)]))
+    assert np.allclose(rf["moments"][0].numpy(), g["ref_moments"], rtol=1e-4)
+    assert np.allclose(rf["points"][0].numpy(), g["ref_pts"], atol=5e-4)
+    sf = sc.principal_frames(torch.from_numpy(g["coords"]), torch.from_numpy(g["n_nodes"]))
+    print("shape moments max rel err", float(np.abs(sf["moments"].numpy() / g["moments"] - 1).max()),
+          "principal coords max abs err", float(np.abs(sf["points"].numpy() - g["pts"]).max()))
+    assert np.allclose(sf["moments"].numpy(), g["moments"], rtol=1e-4)
+    assert np.allclose(sf["points"].numpy(), g["pts"], atol=5e-4)   # same eigh, same sign / order conventions
+
+
+def test_shape_tanimoto_golden(engines):
+    g = golden("shape")
+    sc = _scorer(engines)
+    out = sc.evaluate(torch.from_numpy(g["ref_xyz"]), torch.from_numpy(g["coords"]), torch.from_numpy(g["n_nodes"]))
+    err = float(np.abs(out["scores"].numpy() - g["scores"]).max())
+    print("shape Tanimoto max abs err over 5 samples x 4 orientations", err)
+    assert err < 2e-4                                              # fp32 grid sums, separable exp: stated tolerance
+    assert np.array_equal(out["best_orientation"].numpy(), g["best_idx"])
+    assert np.allclose(out["shape_tanimoto"].numpy(), g["scores"].max(1), atol=2e-4)
+    assert np.allclose(out["aligned_coords"].numpy(), g["best_coord"], atol=5e-4)
+    assert np.allclose(out["reference_coords"].numpy(), g["ref_pts"], atol=5e-4)
+
+
+def test_shape_self_similarity_and_batch_invariance(engines):
+    """A molecule scores 1 against itself; a sample's scores do not depend on what else is in the batch or on padding."""
+    g = golden("shape")
+    sc = _scorer(engines)
+    ref = torch.from_numpy(g["ref_xyz"])
+    one = sc.evaluate(ref, ref.unsqueeze(0), torch.tensor([ref.size(0)]))
+    assert abs(float(one["shape_tanimoto"][0]) - 1.0) < 1e-5 and int(one["best_orientation"][0]) == 0
+    coords, n = torch.from_numpy(g["coords"]), torch.from_numpy(g["n_nodes"])
+    full = sc.evaluate(ref, coords, n)["scores"]
+    padded = torch.zeros(2, 40, 3)
+    padded[0, :coords.size(1)] = coords[3]
+    padded[1, :coords.size(1)] = coords[1]
+    part = sc.evaluate(ref, padded, n[[3, 1]])["scores"]
+    assert torch.equal(part[0], full[3]) and torch.equal(part[1], full[1])

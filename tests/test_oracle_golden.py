@@ -82,3 +82,19 @@ def test_step_scalars_match_oracle():
         a, b = step_scalars(gam, s), O.step_coefficients(gam, s)
         assert a["t"] == b["t"] and a["alpha_ts"] == b["alpha_ts"] and a["c_eps"] == b["eps_coef"]
         assert a["c_sigma"] == b["sigma"] and a["alpha_s"] == b["alpha_s"] and a["sigma_s"] == b["sigma_s"]
+
+
+def test_shape_oracle_against_reference():
+    """oracle/shape_oracle.py (Gaussian shape quadrupole frame + grid Tanimoto, reference shape_similarity.py and
+    pipeline.py:37-86) against vectors produced by the reference's own functions."""
+    from oracle import shape_oracle as S
+    g = golden("shape")
+    ref = torch.from_numpy(g["ref_xyz"])
+    mom, pts = S.shape_quadrupole(ref - ref.mean(0))
+    assert np.allclose(mom.numpy(), g["ref_moments"], rtol=1e-5) and np.allclose(pts.numpy(), g["ref_pts"], atol=1e-5)
+    for b in range(len(g["n_nodes"])):
+        n = int(g["n_nodes"][b])
+        scores, best, coord, _ = S.evaluate_shape(ref, torch.from_numpy(g["coords"][b, :n]))
+        assert np.allclose(scores, g["scores"][b], atol=2e-6), (b, scores, g["scores"][b])
+        assert best == int(g["best_idx"][b])
+        assert np.allclose(coord.numpy(), g["best_coord"][b, :n], atol=2e-5)
