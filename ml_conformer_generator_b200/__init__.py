@@ -3,12 +3,14 @@ the EGNN denoiser + AdjMatSeer bond GCN) behind the reference's `MLConformerGene
 from .config import ATOM_DECODER, CONTEXT_NORMS, DIMENSION, MAX_N_NODES, MIN_N_NODES, NUM_BOND_TYPES  # noqa: F401
 from .conformer_generator import MLConformerGenerator  # noqa: F401
 from .engine import Engine, MlcgError  # noqa: F401
+from .shape_similarity import ShapeScorer  # noqa: F401
 
 
 def evaluate_samples(*args, **kwargs):
-    """Re-export of the reference's CPU scoring pipeline (cheminformatics/pipeline.py:17-96).  Shape / chemical
-    Tanimoto scoring stays on CPU with RDKit (out of scope of the accelerated path); this forwards to the reference
-    package when it is installed."""
+    """Re-export of the reference's scoring pipeline (cheminformatics/pipeline.py:17-96), which needs RDKit for the Morgan
+    fingerprints and the mol blocks; this forwards to the reference package when it is installed.  The tensor part of
+    it -- principal shape-quadrupole frames and the 4-orientation grid Tanimoto -- runs on the GPU through
+    `ShapeScorer.evaluate(reference_coord, sample_coords, n_nodes)` without RDKit."""
     try:
         from mlconfgen import evaluate_samples as _ref
     except ImportError as exc:
@@ -16,4 +18,4 @@ def evaluate_samples(*args, **kwargs):
     return _ref(*args, **kwargs)
 
 
-__all__ = ["MLConformerGenerator", "Engine", "MlcgError", "evaluate_samples"]
+__all__ = ["MLConformerGenerator", "Engine", "MlcgError", "ShapeScorer", "evaluate_samples"]
