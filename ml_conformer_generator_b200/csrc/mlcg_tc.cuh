@@ -913,11 +913,20 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           long long s0 = profiling ? clock64() : 0;
           float* gates = trs_all;  // [128]; the coordinate-message buffer is unused by GCL layers
           if (qq == 0) gates[r] = gate;
-          // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8
-          auto readout = [&](int cb) {
+          // D2 readout: lane r = MMA row m, columns = groups; quarter qq stores groups g = qq, qq+4, qq+8.  First all four
+          // blocks are pulled out of TMEM (3 values per block and thread), then D is released -- the next tile's MMAs start
+          // while the global stores below are still in flight.
+          float dval[4][3];
+          auto readout_ld = [&](int cb) {
             float v[16];
             tmem_ld16(trow + cb * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), v);
             tmem_wait_ld();
+            // select v[qq + 4 gi] without dynamic register indexing
+            dval[cb][0] = qq == 0 ? v[0] : qq == 1 ? v[1] : qq == 2 ? v[2] : v[3];
+            dval[cb][1] = qq == 0 ? v[4] : qq == 1 ? v[5] : qq == 2 ? v[6] : v[7];
+            dval[cb][2] = qq == 0 ? v[8] : qq == 1 ? v[9] : qq == 2 ? v[10] : v[11];
+          };
+          auto readout_st = [&](int cb) {
             const int ch = (cb < 3) ? 112 * (r >> 5) + 32 * cb + (r & 31) : 112 * (r >> 4) + 96 + (r & 15);
             if (cb < 3 || r < 64) {
               uint8_t* cbase = p.agg_op + (size_t)(ch >> 6) * A_CHUNK_BYTES + (ch & 7) * 2;
@@ -929,17 +938,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
                   const int node = node0 + i0 + g;
                   uint8_t* dst = cbase + (size_t)(node >> 7) * p.agg_chunks * A_CHUNK_BYTES + (node & 127) * 128 +
                                  ((rd_piece ^ (node & 7)) << 4);
-                  // select v[g] without dynamic register indexing
-                  const float val = (gi == 0) ? (qq == 0 ? v[0] : qq == 1 ? v[1] : qq == 2 ? v[2] : v[3])
-                                  : (gi == 1) ? (qq == 0 ? v[4] : qq == 1 ? v[5] : qq == 2 ? v[6] : v[7])
-                                              : (qq == 0 ? v[8] : qq == 1 ? v[9] : qq == 2 ? v[10] : v[11]);
+                  const float val = dval[cb][gi];
                   const int fx = gfix(g);
                   if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + ch, val);
                   else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
                 }
               }
             }
-            tc_fence_before();
           };
           named_bar_sync(1, EDGE_CT);  // all gates written; every thread's pass-1 staging stores are issued
           if (ct >= 256) {
@@ -970,10 +975,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           tc_fence_after();
           if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }   // segment-sum MMAs
 #pragma unroll
-          for (int cb = 0; cb < 4; ++cb) readout(cb);
+          for (int cb = 0; cb < 4; ++cb) readout_ld(cb);
           // D (which held the segment sums) is free: the next tile's MMAs may start
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) arrive_leader(d_empty);
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) readout_st(cb);
           if (profiling) { long long c = clock64(); pacc[10] += c - s0; s0 = c; }
         } else {
 #pragma unroll 1
