@@ -917,14 +917,18 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // blocks are pulled out of TMEM (3 values per block and thread), then D is released -- the next tile's MMAs start
           // while the global stores below are still in flight.
           float dval[4][3];
-          auto readout_ld = [&](int cb) {
-            float v[16];
+          auto readout_ld2 = [&](int cb) {  // blocks cb and cb+1: both TMEM loads in flight
+            float v[16], u[16];
             tmem_ld16(trow + cb * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), v);
+            tmem_ld16(trow + (cb + 1) * (kPair ? 32 : 16) + (kPair ? crank * 16 : 0), u);
             tmem_wait_ld();
-            // select v[qq + 4 gi] without dynamic register indexing
+            // select [qq + 4 gi] without dynamic register indexing
             dval[cb][0] = qq == 0 ? v[0] : qq == 1 ? v[1] : qq == 2 ? v[2] : v[3];
             dval[cb][1] = qq == 0 ? v[4] : qq == 1 ? v[5] : qq == 2 ? v[6] : v[7];
             dval[cb][2] = qq == 0 ? v[8] : qq == 1 ? v[9] : qq == 2 ? v[10] : v[11];
+            dval[cb + 1][0] = qq == 0 ? u[0] : qq == 1 ? u[1] : qq == 2 ? u[2] : u[3];
+            dval[cb + 1][1] = qq == 0 ? u[4] : qq == 1 ? u[5] : qq == 2 ? u[6] : u[7];
+            dval[cb + 1][2] = qq == 0 ? u[8] : qq == 1 ? u[9] : qq == 2 ? u[10] : u[11];
           };
           auto readout_st = [&](int cb) {
             const int ch = (cb < 3) ? 112 * (r >> 5) + 32 * cb + (r & 31) : 112 * (r >> 4) + 96 + (r & 15);
@@ -974,8 +978,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           mbar_wait(e_done(0), (uint32_t)(it & 1));
           tc_fence_after();
           if (profiling) { long long c = clock64(); pacc[7] += c - s0; s0 = c; }   // segment-sum MMAs
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb) readout_ld(cb);
+          readout_ld2(0);
+          readout_ld2(2);
           // D (which held the segment sums) is free: the next tile's MMAs may start
           tc_fence_before();
           __syncwarp();
