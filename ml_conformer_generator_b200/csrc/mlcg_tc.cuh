@@ -171,6 +171,12 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
       auto stg_at = [&](int r, int pc) { return stg + r * 128 + ((pc ^ (r & 7)) << 4); };
       const int row0 = mt * TILE_M + q * 32;  // first global row of this warp
       uint32_t ow[32];                        // packed words of the current 128-byte output block (thread's row)
+      [[maybe_unused]] uint4 rnext[8];        // EPI_RESID_OP: prefetched residual block of the next column group
+      if constexpr (kEpi == EPI_RESID_OP) {
+        const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, nt * BN, 0));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rnext[i] = nblk[i * 32 + lane];
+      }
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld32(trow + c0, v);
@@ -178,11 +184,16 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
         const int gcol = nt * BN + c0;
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
         if constexpr (kEpi == EPI_RESID_OP) {
-          // residual block of the warp: 32 rows x 32 floats, contiguous 4 KB in the tiled layout
+          // residual block of the warp: 32 rows x 32 floats, contiguous 4 KB in the tiled layout; the block of the next
+          // column group is already in flight (rnext), so the global-load latency is paid once per tile, not per group
           float* rblk = p.resid + hres_index(row0, gcol, 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<uint4*>(stg_at(4 * i + crow, cpiece)) = reinterpret_cast<const uint4*>(rblk)[i * 32 + lane];
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stg_at(4 * i + crow, cpiece)) = rnext[i];
+          if (c0 + 32 < BN) {
+            const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, gcol + 32, 0));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rnext[i] = nblk[i * 32 + lane];
+          }
           __syncwarp();
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
