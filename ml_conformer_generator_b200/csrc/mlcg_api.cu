@@ -132,7 +132,7 @@ static cudaError_t launch_gemm(const GemmArgs& a, int n_mtiles, int n_ntiles, cu
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_tc_gemm<kMode, BN, kEpi><<<dim3(n_mtiles, n_ntiles), 192, GemmCfg<BN>::SMEM_BYTES, st>>>(a);
+  k_tc_gemm<kMode, BN, kEpi><<<dim3(n_mtiles, n_ntiles), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(a);
   return cudaGetLastError();
 }
 template <int BN, int kEpi>

@@ -51,8 +51,13 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// warp 0 = producer, warp 1 = MMA issuer, then 4 * GEMM_NSUB epilogue warps: warp w reads TMEM lanes 32*(w%4).. and every
+// GEMM_NSUB-th 128-byte output block (the staged epilogue is latency bound per warp, so two warps share a lane quarter)
+constexpr int GEMM_NSUB = 2;
+constexpr int GEMM_THREADS = 64 + 128 * GEMM_NSUB;
+
 template <int kMode, int BN, int kEpi>
-__global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr bool kFast = (kMode == PREC_BF16);
   extern __shared__ uint8_t smem_raw[];
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
     if constexpr (kEpi == EPI_F32) {
       float rs = 1.0f;
       if (p.rowscale != nullptr && rvalid) rs = p.rowscale[grow];
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = ((warp - 2) >> 2) * 32; c0 < BN; c0 += 32 * GEMM_NSUB) {
         float v[32];
         tmem_ld32(trow + c0, v);
         tmem_wait_ld();
@@ -166,18 +171,26 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
       // from global memory with lane = (row 4i + lane/8, piece lane%8): 4 full 128-byte lines per instruction.  The
       // staging lives in the first ring stage, which is idle once the last MMA has completed.
       constexpr int EPC = epc(kMode);
-      uint8_t* stg = gen_base + q * 4096;
+      constexpr int UNIT = EPC / 32;             // 32-column accumulator groups per 128-byte output block
+      constexpr int NBLK = BN / EPC;             // output blocks per row
+      const int sub = (warp - 2) >> 2;           // this warp handles blocks sub, sub + GEMM_NSUB, ...
+      const int n_my = ((NBLK - sub + GEMM_NSUB - 1) / GEMM_NSUB) * UNIT;  // its number of 32-column groups
+      auto group_c0 = [&](int k) { return ((sub + GEMM_NSUB * (k / UNIT)) * UNIT + (k % UNIT)) * 32; };
+      uint8_t* stg = gen_base + (sub * 4 + q) * 4096;
       const int crow = lane >> 3, cpiece = lane & 7;
       auto stg_at = [&](int r, int pc) { return stg + r * 128 + ((pc ^ (r & 7)) << 4); };
       const int row0 = mt * TILE_M + q * 32;  // first global row of this warp
       uint32_t ow[32];                        // packed words of the current 128-byte output block (thread's row)
       [[maybe_unused]] uint4 rnext[8];        // EPI_RESID_OP: prefetched residual block of the next column group
       if constexpr (kEpi == EPI_RESID_OP) {
-        const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, nt * BN, 0));
+        if (n_my > 0) {
+          const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, nt * BN + group_c0(0), 0));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rnext[i] = nblk[i * 32 + lane];
+          for (int i = 0; i < 8; ++i) rnext[i] = nblk[i * 32 + lane];
+        }
       }
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int gk = 0; gk < n_my; ++gk) {
+        const int c0 = group_c0(gk);
         float v[32];
         tmem_ld32(trow + c0, v);
         tmem_wait_ld();
@@ -189,8 +202,8 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const GemmArgs p) {
           float* rblk = p.resid + hres_index(row0, gcol, 0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stg_at(4 * i + crow, cpiece)) = rnext[i];
-          if (c0 + 32 < BN) {
-            const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, gcol + 32, 0));
+          if (gk + 1 < n_my) {
+            const uint4* nblk = reinterpret_cast<const uint4*>(p.resid + hres_index(row0, nt * BN + group_c0(gk + 1), 0));
 #pragma unroll
             for (int i = 0; i < 8; ++i) rnext[i] = nblk[i * 32 + lane];
           }
