@@ -53,7 +53,10 @@ struct GemmCfg {
 
 // warp 0 = producer, warp 1 = MMA issuer, then 4 * GEMM_NSUB epilogue warps: warp w reads TMEM lanes 32*(w%4).. and every
 // GEMM_NSUB-th 128-byte output block (the staged epilogue is latency bound per warp, so two warps share a lane quarter)
-constexpr int GEMM_NSUB = 2;
+#ifndef MLCG_GEMM_NSUB
+#define MLCG_GEMM_NSUB 2
+#endif
+constexpr int GEMM_NSUB = MLCG_GEMM_NSUB;
 constexpr int GEMM_THREADS = 64 + 128 * GEMM_NSUB;
 
 template <int kMode, int BN, int kEpi>
