@@ -132,7 +132,17 @@ static cudaError_t launch_gemm(const GemmArgs& a, int n_mtiles, int n_ntiles, cu
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  k_tc_gemm<kMode, BN, kEpi><<<dim3(n_mtiles, n_ntiles), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(a);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  GemmArgs b = a;
+  b.n_mtiles = n_mtiles;
+  b.n_ntiles = n_ntiles;
+  k_tc_gemm<kMode, BN, kEpi><<<std::min(n_mtiles * n_ntiles, num_sms), GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(b);
   return cudaGetLastError();
 }
 template <int BN, int kEpi>

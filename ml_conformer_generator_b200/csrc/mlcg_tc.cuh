@@ -39,6 +39,7 @@ struct GemmArgs {
   int out_op_chunks;
   float* resid;           // EPI_RESID_OP: fp32 residual stream, updated in place
   int ldr;
+  int n_mtiles, n_ntiles; // tile grid (set by the launcher); the kernel is persistent and walks it with stride gridDim.x
 };
 
 template <int BN>
@@ -70,10 +71,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::NSTAGE + s); };
   const uint32_t dfull_bar = bar0 + 8u * (2 * Cfg::NSTAGE);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + Cfg::NSTAGE * Cfg::STAGE_BYTES + 8 * (2 * Cfg::NSTAGE + 1));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen_base + Cfg::NSTAGE * Cfg::STAGE_BYTES + 8 * (2 * Cfg::NSTAGE + 2));
 
+  const uint32_t epi_done = dfull_bar + 8u;   // all epilogue warps are done with the accumulator and the staging of a tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int n_tiles = p.n_mtiles * p.n_ntiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NSTAGE; ++s) {
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(dfull_bar, 1);
+    mbar_init(epi_done, 4 * GEMM_NSUB);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
@@ -89,50 +92,81 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent: CTA b handles tiles b, b + gridDim.x, ... (tile = m-tile * n_ntiles + n-tile).  Chunk kc of a tile goes to
+  // ring slot (kc + 1) % NSTAGE, so slot 0 -- whose memory doubles as the epilogue staging -- is the last one a tile
+  // needs: while the epilogue of tile t runs, the producer already prefetches the first NSTAGE - 1 chunks of tile t + 1.
+  // uses[s] counts how often slot s has been filled (mbarrier phase bookkeeping), kept in registers.
   if (warp == 0) {
     if (lane == 0) {
-      for (int kc = 0; kc < p.n_kc; ++kc) {
-        const int s = kc % Cfg::NSTAGE;
-        const uint32_t ph = (kc / Cfg::NSTAGE) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_arrive_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-        const uint8_t* asrc = (kc < p.a0_chunks)
-                                  ? p.a0 + ((size_t)mt * p.a0_per_tile + kc) * A_CHUNK_BYTES
-                                  : p.a1 + ((size_t)mt * p.a1_per_tile + (kc - p.a0_chunks)) * A_CHUNK_BYTES;
-        const uint8_t* wsrc = p.w + ((size_t)nt * p.n_kc + kc) * (size_t)(BN * CHUNK_BYTES);
-        const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-        bulk_g2s(sa, asrc, A_CHUNK_BYTES, full_bar(s));
-        bulk_g2s(sa + A_CHUNK_BYTES, wsrc, BN * CHUNK_BYTES, full_bar(s));
+      uint32_t uses[Cfg::NSTAGE];
+#pragma unroll
+      for (int s = 0; s < Cfg::NSTAGE; ++s) uses[s] = 0;
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const int sl = (kc + 1) % Cfg::NSTAGE;
+          if (tl > 0 && kc == Cfg::NSTAGE - 1) mbar_wait(epi_done, (uint32_t)((tl - 1) & 1));  // staging (slot 0) is free again
+          uint32_t u = 0;
+#pragma unroll
+          for (int s = 0; s < Cfg::NSTAGE; ++s)
+            if (s == sl) { u = uses[s]; uses[s]++; }
+          mbar_wait(empty_bar(sl), (u & 1u) ^ 1u);
+          mbar_arrive_expect_tx(full_bar(sl), Cfg::STAGE_BYTES);
+          const uint8_t* asrc = (kc < p.a0_chunks)
+                                    ? p.a0 + ((size_t)mt * p.a0_per_tile + kc) * A_CHUNK_BYTES
+                                    : p.a1 + ((size_t)mt * p.a1_per_tile + (kc - p.a0_chunks)) * A_CHUNK_BYTES;
+          const uint8_t* wsrc = p.w + ((size_t)nt * p.n_kc + kc) * (size_t)(BN * CHUNK_BYTES);
+          const uint32_t sa = base + sl * Cfg::STAGE_BYTES;
+          bulk_g2s(sa, asrc, A_CHUNK_BYTES, full_bar(sl));
+          bulk_g2s(sa + A_CHUNK_BYTES, wsrc, BN * CHUNK_BYTES, full_bar(sl));
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, TILE_M, Cfg::NPER);
-      for (int kc = 0; kc < p.n_kc; ++kc) {
-        const int s = kc % Cfg::NSTAGE;
-        const uint32_t ph = (kc / Cfg::NSTAGE) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = base + s * Cfg::STAGE_BYTES;
-        const uint64_t adesc = umma_desc_sw128(sa);
+      uint32_t uses[Cfg::NSTAGE];
 #pragma unroll
-        for (int nh = 0; nh < Cfg::NH; ++nh) {
-          const uint64_t bdesc = umma_desc_sw128(sa + A_CHUNK_BYTES + nh * Cfg::NPER * CHUNK_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma<kMode>(tmem_base + nh * Cfg::NPER, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+      for (int s = 0; s < Cfg::NSTAGE; ++s) uses[s] = 0;
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        if (tl > 0) {  // the previous tile's accumulator has been read out
+          mbar_wait(epi_done, (uint32_t)((tl - 1) & 1));
+          tc_fence_after();
         }
-        umma_commit(empty_bar(s));
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const int sl = (kc + 1) % Cfg::NSTAGE;
+          uint32_t u = 0;
+#pragma unroll
+          for (int s = 0; s < Cfg::NSTAGE; ++s)
+            if (s == sl) { u = uses[s]; uses[s]++; }
+          mbar_wait(full_bar(sl), u & 1u);
+          tc_fence_after();
+          const uint32_t sa = base + sl * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_sw128(sa);
+#pragma unroll
+          for (int nh = 0; nh < Cfg::NH; ++nh) {
+            const uint64_t bdesc = umma_desc_sw128(sa + A_CHUNK_BYTES + nh * Cfg::NPER * CHUNK_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma<kMode>(tmem_base + nh * Cfg::NPER, adesc + 2 * ks, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+          }
+          umma_commit(empty_bar(sl));
+        }
+        umma_commit(dfull_bar);
       }
-      umma_commit(dfull_bar);
     }
   } else {
+   int tl = 0;
+   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+    const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int grow = mt * TILE_M + row;
     const bool rvalid = grow < p.m_rows;
-    mbar_wait(dfull_bar, 0);
+    mbar_wait(dfull_bar, (uint32_t)(tl & 1));
     tc_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     if constexpr (kEpi == EPI_F32) {
@@ -281,6 +315,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         }
       }
     }
+    // this warp is done with the tile's accumulator and staging
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(epi_done);
+   }
   }
   tc_fence_before();
   __syncthreads();
