@@ -49,7 +49,8 @@ struct GemmCfg {
   static constexpr int NH = BN / NPER;
   static constexpr int STAGE_BYTES = A_CHUNK_BYTES + BN * CHUNK_BYTES;
   static constexpr int TMEM_COLS = (BN > 256) ? 512 : 256;
-  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int BIAS_OFF = NSTAGE * STAGE_BYTES + 256;  // after the barriers: bias of the tile's BN columns, double-buffered
+  static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4;
 };
 
 // warp 0 = producer, warp 1 = MMA issuer, then 4 * GEMM_NSUB epilogue warps: warp w reads TMEM lanes 32*(w%4).. and every
@@ -161,6 +162,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
    int tl = 0;
    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
     const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
+    // bias of this tile's columns -> shared memory while the main loop runs (a global load inside the column loop would
+    // expose its latency once per 32 columns).  Double-buffered by tile parity; the named barrier orders buffer reuse.
+    float* bias_s = reinterpret_cast<float*>(gen_base + Cfg::BIAS_OFF) + (tl & 1) * BN;
+    for (int i = threadIdx.x - 64; i < BN; i += GEMM_THREADS - 64) bias_s[i] = p.bias[nt * BN + i];
+    named_bar_sync(1, GEMM_THREADS - 64);
     // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31; thread = one output row
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -178,11 +184,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         tmem_wait_ld();
         const int gcol = nt * BN + c0;
         if (rvalid) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
           float* orow = p.out_f32 + (size_t)grow * p.ldo + gcol;
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
-            const float4 b = __ldg(b4 + (e >> 2));
+            const float4 b = b4[e >> 2];
             float4 o;
             o.x = fmaf(rs, b.x, v[e + 0]);
             o.y = fmaf(rs, b.y, v[e + 1]);
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         tmem_ld32(trow + c0, v);
         tmem_wait_ld();
         const int gcol = nt * BN + c0;
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + gcol);
+        const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
         if constexpr (kEpi == EPI_RESID_OP) {
           // residual block of the warp: 32 rows x 32 floats, contiguous 4 KB in the tiled layout; the block of the next
           // column group is already in flight (rnext), so the global-load latency is paid once per tile, not per group
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
           __syncwarp();
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
-            const float4 b = __ldg(b4 + (e >> 2));
+            const float4 b = b4[e >> 2];
             float4 h = *reinterpret_cast<const float4*>(stg_at(lane, e >> 2));
             h.x += v[e + 0] + b.x;
             h.y += v[e + 1] + b.y;
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         } else {
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
-            const float4 b = __ldg(b4 + (e >> 2));
+            const float4 b = b4[e >> 2];
             if constexpr (kEpi == EPI_SILU_OP) {
               v[e + 0] = silu<kFast>(v[e + 0] + b.x); v[e + 1] = silu<kFast>(v[e + 1] + b.y);
               v[e + 2] = silu<kFast>(v[e + 2] + b.z); v[e + 3] = silu<kFast>(v[e + 3] + b.w);
