@@ -752,22 +752,22 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = h->kc448();
   if (h->precision == PREC_BF16)
-    k_egnn_prepare<PREC_BF16><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->w_emb.d,
+    k_egnn_prepare<PREC_BF16><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M, h->w_emb.d,
                                                   h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
                                                   h->x0.as<float>(), h->xa.as<float>());
   else if (h->precision == PREC_TF32)
-    k_egnn_prepare<PREC_TF32><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->w_emb.d,
+    k_egnn_prepare<PREC_TF32><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M, h->w_emb.d,
                                                   h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
                                                   h->x0.as<float>(), h->xa.as<float>());
   else
-    k_egnn_prepare<PREC_FP32_SIMT><<<h->M, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N,
+    k_egnn_prepare<PREC_FP32_SIMT><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M,
                                                        h->w_emb.d, h->b_emb.d, h->h_res.as<float>(), HP, nullptr, 0,
                                                        h->x0.as<float>(), h->xa.as<float>());
   KCHECK();
   int rc = (h->precision == PREC_FP32_SIMT) ? egnn_forward_simt(h, st) : egnn_forward_tc(h, st);
   if (rc) return rc;
   // 9 blocks: blocks 0,2,4,6,8 write xb -> final coordinates are in xb
-  k_egnn_readout<<<h->B, 128, 0, st>>>(h->h_res.as<float>(), h->precision == PREC_FP32_SIMT ? HP : 0, h->xb.as<float>(), h->x0.as<float>(), h->d_n_nodes.as<int>(),
+  k_egnn_readout<<<h->B, 256, 0, st>>>(h->h_res.as<float>(), h->precision == PREC_FP32_SIMT ? HP : 0, h->xb.as<float>(), h->x0.as<float>(), h->d_n_nodes.as<int>(),
                                        h->d_node_off.as<int>(), h->N, h->w_out.d, h->b_out.d, eps);
   KCHECK();
   return MLCG_OK;

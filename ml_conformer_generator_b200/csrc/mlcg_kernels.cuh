@@ -239,37 +239,51 @@ __global__ void k_decode(const float* __restrict__ z0, const float* __restrict__
 // EGNN prepare (mask, split, time/context append, 12->420 embedding) and readout (420->8, velocity, COM removal)
 // reference egnn.py:472-513, 315, 398-399
 // =================================================================================================================
+constexpr int PREP_NPB = 8;  // nodes per block of k_egnn_prepare
 template <int kMode>
 __global__ void __launch_bounds__(HP) k_egnn_prepare(const float* __restrict__ z, const float* __restrict__ t,
                                                       const float* __restrict__ ctx, const int* __restrict__ node_mol,
-                                                      const int* __restrict__ node_off, int N, const float* __restrict__ w_emb,
-                                                      const float* __restrict__ b_emb, float* __restrict__ h_res, int ldh,
-                                                      uint8_t* __restrict__ h_op, int op_chunks, float* __restrict__ x0,
-                                                      float* __restrict__ x_cur) {
-  const int node = blockIdx.x, c = threadIdx.x;
-  const int b = node_mol[node], i = node - node_off[b];
-  const float* zp = z + ((size_t)b * N + i) * ZC;
-  __shared__ float hin[IN_NF];
-  if (c < 8) hin[c] = zp[3 + c];
-  if (c == 8) hin[8] = t[b];
-  if (c >= 9 && c < 12) hin[c] = ctx[b * 3 + (c - 9)];
-  if (c >= 12 && c < 15) {
-    const float v = zp[c - 12];
-    x0[(size_t)node * 3 + (c - 12)] = v;
-    x_cur[(size_t)node * 3 + (c - 12)] = v;
+                                                      const int* __restrict__ node_off, int N, int M,
+                                                      const float* __restrict__ w_emb, const float* __restrict__ b_emb,
+                                                      float* __restrict__ h_res, int ldh, uint8_t* __restrict__ h_op,
+                                                      int op_chunks, float* __restrict__ x0, float* __restrict__ x_cur) {
+  const int c = threadIdx.x, nbase = blockIdx.x * PREP_NPB;
+  __shared__ float hin[PREP_NPB][IN_NF];
+  if (c < PREP_NPB * 15) {  // thread = (node of the block, one of its 12 inputs or 3 coordinates)
+    const int nl = c / 15, k = c - nl * 15, node = nbase + nl;
+    if (node < M) {
+      const int b = node_mol[node], i = node - node_off[b];
+      const float* zp = z + ((size_t)b * N + i) * ZC;
+      if (k < 8) hin[nl][k] = zp[3 + k];
+      else if (k == 8) hin[nl][8] = t[b];
+      else if (k < 12) hin[nl][k] = ctx[b * 3 + (k - 9)];
+      else {
+        const float v = zp[k - 12];
+        x0[(size_t)node * 3 + (k - 12)] = v;
+        x_cur[(size_t)node * 3 + (k - 12)] = v;
+      }
+    }
   }
   __syncthreads();
-  float acc = 0.f;
-  if (c < HID) {
-    acc = b_emb[c];
+  float w[IN_NF], bias = 0.f;  // this channel's embedding row stays in registers for the block's nodes
 #pragma unroll
-    for (int k = 0; k < IN_NF; ++k) acc = fmaf(w_emb[c * IN_NF + k], hin[k], acc);
+  for (int k = 0; k < IN_NF; ++k) w[k] = (c < HID) ? w_emb[c * IN_NF + k] : 0.f;
+  if (c < HID) bias = b_emb[c];
+  for (int nl = 0; nl < PREP_NPB; ++nl) {
+    const int node = nbase + nl;
+    if (node >= M) break;
+    float acc = 0.f;
+    if (c < HID) {
+      acc = bias;
+#pragma unroll
+      for (int k = 0; k < IN_NF; ++k) acc = fmaf(w[k], hin[nl][k], acc);
+    }
+    h_res[hres_index(node, c, ldh)] = acc;
+    if constexpr (kMode != PREC_FP32_SIMT) op_store1<kMode>(h_op, op_chunks, node, c, acc);
   }
-  h_res[hres_index(node, c, ldh)] = acc;
-  if constexpr (kMode != PREC_FP32_SIMT) op_store1<kMode>(h_op, op_chunks, node, c, acc);
 }
 
-__global__ void __launch_bounds__(128) k_egnn_readout(const float* __restrict__ h_res, int ldh, const float* __restrict__ x_fin,
+__global__ void __launch_bounds__(256) k_egnn_readout(const float* __restrict__ h_res, int ldh, const float* __restrict__ x_fin,
                                                        const float* __restrict__ x0, const int* __restrict__ n_nodes,
                                                        const int* __restrict__ node_off, int N, const float* __restrict__ w_out,
                                                        const float* __restrict__ b_out, float* __restrict__ eps) {
@@ -292,15 +306,40 @@ __global__ void __launch_bounds__(128) k_egnn_readout(const float* __restrict__ 
     const int i = idx / 3, c = idx - i * 3;
     eps[((size_t)b * N + i) * ZC + c] = (i < n) ? vel[idx] - mean[c] : 0.f;
   }
-  // class channels: only the first 8 of the 12 embedding_out rows reach eps (reference egnn.py:503-505)
-  for (int d = warp; d < N * 8; d += 4) {
-    const int i = d >> 3, o = d & 7;
-    float acc = 0.f;
+  // class channels: only the first 8 of the 12 embedding_out rows reach eps (reference egnn.py:503-505).
+  // One warp per atom: its h row is loaded once (14 independent loads per lane), the 8 output rows come from shared memory.
+  __shared__ float wo[8 * HID];
+  for (int idx = threadIdx.x; idx < 8 * HID; idx += blockDim.x) wo[idx] = w_out[idx];
+  __syncthreads();
+  const int nwarps = blockDim.x >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0.f;
     if (i < n) {
-      for (int k = lane; k < HID; k += 32) acc = fmaf(w_out[o * HID + k], h_res[hres_index(node0 + i, k, ldh)], acc);
-      acc = warp_sum(acc) + b_out[o];
+      float hv[(HID + 31) / 32];
+#pragma unroll
+      for (int kk = 0; kk < (HID + 31) / 32; ++kk) {
+        const int k = lane + 32 * kk;
+        hv[kk] = (k < HID) ? h_res[hres_index(node0 + i, k, ldh)] : 0.f;
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+#pragma unroll
+        for (int kk = 0; kk < (HID + 31) / 32; ++kk) {
+          const int k = lane + 32 * kk;
+          if (k < HID) acc[o] = fmaf(wo[o * HID + k], hv[kk], acc[o]);  // same order as a per-lane loop k = lane, lane+32, ...
+        }
+        acc[o] = warp_sum(acc[o]) + b_out[o];
+      }
     }
-    if (lane == 0) eps[((size_t)b * N + i) * ZC + 3 + o] = acc;
+    if (lane < 8) {
+      float v = 0.f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o)
+        if (lane == o) v = acc[o];
+      eps[((size_t)b * N + i) * ZC + 3 + lane] = v;
+    }
   }
 }
 
