@@ -111,3 +111,34 @@ def test_generate_sdf(generators):
         assert 15 <= len(sym) <= 19 and xyz.shape == (len(sym), 3) and torch.isfinite(xyz).all()
         assert all(s in ("C", "N", "O", "F", "P", "S", "Cl", "Br") for s in sym)
         assert all(0 <= a < b < len(sym) and 1 <= o <= 4 for a, b, o in bonds)
+
+
+def test_generate_then_score_shapes(generators):
+    """The downstream half of the reference's README flow without RDKit: generate conformers for a reference context, then
+    score their Gaussian shape similarity against the reference conformer on the GPU (ShapeScorer = the tensor part of
+    evaluate_samples).  Checks consistency, not chemistry: scores in (0, 1], aligned coordinates keep all pair distances."""
+    from ml_conformer_generator_b200 import ShapeScorer
+    g = golden("host_utils")
+    gen = generators(4, "bf16")
+    ref_xyz = torch.from_numpy(g["ceyyag_xyz"])
+    out = gen.generate_tensors(torch.from_numpy(g["ceyyag_context"]), n_atoms=17, n_samples=8, variance=2)
+    scorer = ShapeScorer(gen.engine)
+    x, n = out["x"].float().cpu(), out["n_nodes"]
+    assert bool(torch.isfinite(x).all())
+    # random weights give conformers of arbitrary size; bring every molecule to the reference's radius of gyration so
+    # that it overlaps the reference's grid at all (the scorer itself is pinned to the reference in test_gpu_properties)
+    rg_ref = float((ref_xyz - ref_xyz.mean(0)).pow(2).sum(1).mean().sqrt())
+    for b in range(x.size(0)):
+        k = int(n[b])
+        c = x[b, :k] - x[b, :k].mean(0)
+        x[b, :k] = c * (rg_ref / float(c.pow(2).sum(1).mean().sqrt()))
+    res = scorer.evaluate(ref_xyz, x, n)
+    s = res["shape_tanimoto"]
+    assert s.shape == (8,) and bool(((s > 0) & (s <= 1.0 + 1e-6)).all())
+    assert bool((res["scores"].max(dim=1).values == s).all())
+    xc = x
+    for b in range(8):
+        k = int(n[b])
+        d0 = torch.cdist(xc[b, :k], xc[b, :k])
+        d1 = torch.cdist(res["aligned_coords"][b, :k], res["aligned_coords"][b, :k])
+        assert float((d0 - d1).abs().max()) < 1e-3 * max(1.0, float(d0.max()))  # a rigid motion (possibly a reflection)
