@@ -202,6 +202,33 @@ static bool edge_pair_mode() {
   }
   return v != 0;
 }
+// grid of the persistent edge kernel: one CTA per SM (MLCG_EDGE_GRID overrides it for scaling experiments)
+static int edge_grid_for(int n_tiles, int num_sms) {
+  int g = std::min(n_tiles, num_sms);
+  if (const char* e = getenv("MLCG_EDGE_GRID")) g = std::max(1, std::min(g, atoi(e)));
+  return g;
+}
+// which CTA processes tile t: the same contiguous ranges k_tc_edge computes from (blockIdx, gridDim, n_tiles)
+static void edge_tile_owner(mlcg_handle* h, int n_tiles, std::vector<int>& owner) {
+  owner.assign(n_tiles, 0);
+  int grid = edge_grid_for(n_tiles, h->num_sms);
+  const bool pair = edge_pair_mode() && grid >= 2;
+  if (pair) grid &= ~1;
+  if (grid <= 0) return;
+  if (pair) {
+    const int npairs = grid / 2;
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int T0 = (int)(((long long)pr * n_tiles) / npairs), T1 = (int)(((long long)(pr + 1) * n_tiles) / npairs);
+      const int n_iter = (T1 - T0 + 1) >> 1;
+      for (int t = T0; t < T1; ++t) owner[t] = 2 * pr + (t >= T0 + n_iter ? 1 : 0);
+    }
+  } else {
+    for (int b = 0; b < grid; ++b) {
+      const int t0 = (int)(((long long)b * n_tiles) / grid), t1 = (int)(((long long)(b + 1) * n_tiles) / grid);
+      for (int t = t0; t < t1; ++t) owner[t] = b;
+    }
+  }
+}
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
@@ -512,17 +539,12 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
     } else {
       // cut the n(n-1) target-major edge rows into near-equal ranges of at most 128 rows
       const int E = n * nm1, T = (E + TILE_M - 1) / TILE_M;
-      int carry = -1;  // split-target id shared with the previous tile
       for (int k = 0; k < T; ++k) {
         const int ra = (int)((long long)k * E / T), rb = (int)((long long)(k + 1) * E / T);
         const int i_first = ra / nm1, i_last = (rb - 1) / nm1;
-        EdgeTile t{b, ra - i_first * nm1, rb - ra, n, i_first, i_last - i_first + 1, carry, -1};
-        if (rb % nm1 != 0) {
-          t.fixb = (int)fix_node.size();
-          fix_node.push_back(node0 + i_last);
-        }
-        carry = t.fixb;
-        tiles.push_back(t);
+        // provisional: fixb = node whose neighbour list is cut at the end of this tile (resolved below)
+        tiles.push_back(EdgeTile{b, ra - i_first * nm1, rb - ra, n, i_first, i_last - i_first + 1, EDGE_WHOLE,
+                                 (rb % nm1 != 0) ? node0 + i_last : EDGE_WHOLE});
       }
     }
     for (int i = 0; i < n; ++i) {
@@ -531,6 +553,24 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
       node_edge_off.push_back((int)(edges + (long long)i * (n - 1)));
     }
     edges += (long long)n * (n - 1);
+  }
+  h->n_etiles = (int)tiles.size();
+  {
+    // Resolve the split targets.  The edge kernel gives every CTA a contiguous tile range (edge_tile_owner mirrors it): a
+    // target cut between two tiles of one CTA is carried in shared memory, one cut between two CTAs goes through the
+    // side buffer + k_edge_fixup.
+    std::vector<int> owner;
+    edge_tile_owner(h, (int)tiles.size(), owner);
+    for (size_t t = 0; t + 1 < tiles.size(); ++t) {
+      if (tiles[t].fixb == EDGE_WHOLE) continue;
+      const int node = tiles[t].fixb;
+      if (owner[t] == owner[t + 1]) {
+        tiles[t].fixb = tiles[t + 1].fixa = EDGE_CARRY;
+      } else {
+        tiles[t].fixb = tiles[t + 1].fixa = (int)fix_node.size();
+        fix_node.push_back(node);
+      }
+    }
   }
   h->n_edges = edges;
   h->M = h->h_node_off[B];
@@ -601,12 +641,7 @@ extern "C" int64_t mlcg_kernel_launches(mlcg_handle* h) { return h ? h->launches
 // ---------------------------------------------------------------------------------------------------------------
 // EGNN forward
 // ---------------------------------------------------------------------------------------------------------------
-// grid of the persistent edge kernel: one CTA per SM (MLCG_EDGE_GRID overrides it for scaling experiments)
-static int edge_grid(mlcg_handle* h) {
-  int g = std::min(h->n_etiles, h->num_sms);
-  if (const char* e = getenv("MLCG_EDGE_GRID")) g = std::max(1, std::min(g, atoi(e)));
-  return g;
-}
+static int edge_grid(mlcg_handle* h) { return edge_grid_for(h->n_etiles, h->num_sms); }
 
 static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, float* x_next) {
   EdgeArgs a{};

@@ -396,12 +396,18 @@ struct EdgeSmemT {
 // One 128-row tile of the edge list of a molecule.  The n(n-1) real edges of a molecule are enumerated target-major
 // (target i, then its n-1 neighbours in ascending order) and cut into ceil(n(n-1)/128) near-equal row ranges, so a tile
 // may start and end in the middle of a target node's neighbour list.  Such a "split" target gets its neighbour sum from
-// two tiles: both add their partial sum into a per-batch fp32 side buffer (exactly two addends onto zero: the result does
-// not depend on their order) and k_edge_fixup turns it into the regular output afterwards.
+// two tiles.  Normally both tiles are consecutive tiles of one CTA and the first partial sum is carried over in shared
+// memory; at the ~150 boundaries between CTAs' tile ranges both tiles add their partial sum into a per-batch fp32 side
+// buffer and k_edge_fixup turns it into the regular output afterwards.  Either way the result is first part + second part
+// (fp32 addition is commutative, the side buffer starts at zero): it does not depend on the grid or on timing.
 struct EdgeTile {
   int mol, off0, nrows, n;   // molecule; neighbours of the first target that precede this tile; rows; atoms
-  int i0, ng, fixa, fixb;    // first target; targets touched; split-target ids of the first / last target or -1
+  int i0, ng, fixa, fixb;    // first target; targets touched; state of the first / last target (see below)
 };
+// fixa / fixb: EDGE_WHOLE = the target's neighbour list does not cross this end of the tile; EDGE_CARRY = it continues in
+// the neighbouring tile and that tile is processed by the same CTA right before / after this one: the partial sum is
+// handed over in shared memory; >= 0 = it continues in a tile of another CTA: side-buffer id for the atomic path.
+constexpr int EDGE_WHOLE = -1, EDGE_CARRY = -2;
 static_assert(sizeof(EdgeTile) == 32, "EdgeTile is fetched as two int4");
 
 struct EdgeArgs {
@@ -768,7 +774,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       // neighbouring tile
       auto glo = [&](int g) { return max(g * nm1 - ti.off0, 0); };
       auto ghi = [&](int g) { return min((g + 1) * nm1 - ti.off0, ti.nrows); };
-      auto gfix = [&](int g) { return (g == 0 && ti.fixa >= 0) ? ti.fixa : (g == ng - 1) ? ti.fixb : -1; };
+      auto gfix = [&](int g) { return (g == 0 && ti.fixa >= 0) ? ti.fixa : (g == ng - 1 && ti.fixb >= 0) ? ti.fixb : -1; };
+      // carried partial sums: written for this tile's last target into buffer (it & 1), read for its first target from
+      // buffer ((it - 1) & 1) -- the unused half of the selector area
+      float* carry_wr = reinterpret_cast<float*>(gbase + EdgeSmem::SEL_OFF + 4096) + (it & 1) * 464;
+      const float* carry_rd = reinterpret_cast<const float*>(gbase + EdgeSmem::SEL_OFF + 4096) + ((it & 1) ^ 1) * 464;
+      auto carried_in = [&](int g) { return g == 0 && ti.fixa == EDGE_CARRY; };
+      auto carried_out = [&](int g) { return g == ng - 1 && ti.fixb == EDGE_CARRY; };
       float* trs = trs_all + buf * TILE_M * 3;
       const float2* ri_d = ri_d_all + buf * TILE_M;
       const int* ri_gj = ri_gj_all + buf * TILE_M;
@@ -971,7 +983,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           for (int e = glo(gg); e < ghi(gg); ++e) s += trs[e * 3 + c];
           const int fx = gfix(gg);
           const size_t idx = (size_t)(node0 + i0 + gg) * 3 + c;
-          if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
+          if (carried_in(gg)) s = carry_rd[448 + c] + s;
+          if (carried_out(gg)) carry_wr[448 + c] = s;
+          else if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
           else p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
         }
         if constexpr (kEarlyA) agen_early();  // D was released above: the next tile's MMAs start as soon as chunk 0 is published
@@ -1014,9 +1028,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
                   const int node = node0 + i0 + g;
                   uint8_t* dst = cbase + (size_t)(node >> 7) * p.agg_chunks * A_CHUNK_BYTES + (node & 127) * 128 +
                                  ((rd_piece ^ (node & 7)) << 4);
-                  const float val = dval[cb][gi];
+                  float val = dval[cb][gi];
                   const int fx = gfix(g);
-                  if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + ch, val);
+                  if (carried_in(g)) val = carry_rd[ch] + val;
+                  if (carried_out(g)) carry_wr[ch] = val;
+                  else if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + ch, val);
                   else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
                 }
               }
@@ -1096,8 +1112,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             for (; e < cnt; ++e) s0 += *reinterpret_cast<const float*>(src + sw128_offset(r0 + e, lane >> 2));
             const int col = (2 * hh + (lane >> 4)) * 112 + ch * 16 + (lane & 15);
             const int fx = gfix(gg);
-            if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + col, (s0 + s1) + (s2 + s3));
-            else op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, col, ((s0 + s1) + (s2 + s3)) / 100.0f);
+            float tot = (s0 + s1) + (s2 + s3);
+            if (carried_in(gg)) tot = carry_rd[col] + tot;
+            if (carried_out(gg)) carry_wr[col] = tot;
+            else if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + col, tot);
+            else op_store1<kMode>(p.agg_op, p.agg_chunks, node0 + i0 + gg, col, tot / 100.0f);
           }
         }
         }
