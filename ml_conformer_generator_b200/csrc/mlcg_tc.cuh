@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
   auto e_full = [&](int b) { return pq_full + 32u + 8u * b; };  // gated messages of a 128-channel block staged
   auto e_done = [&](int b) { return pq_full + 48u + 8u * b; };  // segment-sum MMA of that block complete
   auto w_peer = [&](int s) { return pq_full + 64u + 8u * s; };  // pair mode: the peer CTA's half of W slot s has landed
+  const uint32_t d_half = e_done(1);  // accumulator columns 0..223 of the tile are final (one N half before d_full)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + EdgeSmem::BAR_OFF + 8 * (2 * EDGE_NWMAX + 2 * EDGE_NA + 8 + EDGE_NW));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -673,6 +674,9 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_ts_pair<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+              // last chunk: the first N half is complete half a chunk before the second; the epilogue warps of columns
+              // 0..223 start on it while the tensor core finishes columns 224..447
+              if (nh == 0 && kc + 1 == p.n_kc) umma_commit_pair(d_half, 3);
             }
             umma_commit_pair(w_empty(ws), 3);
             ++wi;
@@ -686,6 +690,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
                 umma_ts<kMode>(tmem_base + nh * 224, a_tmem + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+              if (nh == 0 && kc + 1 == p.n_kc) umma_commit(d_half);
               umma_commit(w_empty(ws));
             }
             umma_commit(a_empty(as));
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       if (profiling) { long long c = clock64(); pacc[1] += c - c0; c0 = c; }  // A generation (incl. back-pressure)
 
       // ---- epilogue pass 1: m = SiLU(D) (written back to TMEM for GCL), partial dot with the gate / coord vector ----
-      mbar_wait(d_full, (uint32_t)(it & 1));
+      mbar_wait(qq < 2 ? d_half : d_full, (uint32_t)(it & 1));  // this thread's output columns are 112*qq .. 112*qq+111
       tc_fence_after();
       if (profiling) { long long c = clock64(); pacc[2] += c - c0; c0 = c; }  // MMA tail
       float dotp[4] = {0.f, 0.f, 0.f, 0.f};
