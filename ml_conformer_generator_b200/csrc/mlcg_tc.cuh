@@ -1,15 +1,16 @@
 // tcgen05 / TMEM kernels of the hot path (sm_100a only).
 //
-//  k_tc_gemm  : C[128-row tile, BN cols] = epilogue(A . W^T).  A and W arrive as pre-swizzled operand-format blocks
-//               through 1-D bulk async copies (UBLKCP) into a multi-stage mbarrier ring; one thread issues
-//               tcgen05.mma with the fp32 accumulator in TMEM; four epilogue warps read it back with tcgen05.ld.
-//               Used for the per-node projections / node MLPs of the EGNN (reference egnn.py:30-34,54-68) and for
-//               the AdjMatSeer linears (reference adj_mat_seer.py:53).
+//  k_tc_gemm  : C[128-row tile, BN cols] = epilogue(A . W^T), persistent over the tile list.  A and W arrive as
+//               pre-swizzled operand-format blocks through 1-D bulk async copies (UBLKCP) into a multi-stage mbarrier
+//               ring; one thread issues tcgen05.mma with the fp32 accumulator in TMEM; eight epilogue warps read it back
+//               with tcgen05.ld and move every 128-byte-per-row block through a swizzled staging block so that global
+//               loads / stores are full lines.  Used for the per-node projections / node MLPs of the EGNN (reference
+//               egnn.py:30-34,54-68) and for the AdjMatSeer linears (reference adj_mat_seer.py:53).
 //  k_tc_edge  : the fused all-pairs edge MLP of one EGNN sub-layer (reference egnn.py:38-52 + 418-437 for GCL,
 //               egnn.py:111-135 for EquivariantUpdate).  Edge tensors never touch HBM: the first-layer activation
-//               SiLU(P_i + Q_j + d2*wc + d02*wd) is generated straight into the swizzled A-operand ring in shared
-//               memory, the 420x420 second layer runs on tcgen05 with the accumulator in TMEM, and SiLU, attention
-//               gate, masked neighbour sum / coordinate update run in the epilogue.
+//               SiLU(P_i + Q_j + d2*wc + d02*wd) is generated straight into an A-operand ring in TMEM, the 420x420
+//               second layer runs on tcgen05 (TS mode, CTA pairs) with the accumulator in TMEM, and SiLU, attention
+//               gate, masked neighbour sum (on the tensor core in bf16 mode) / coordinate update run in the epilogue.
 #pragma once
 #include "mlcg_common.cuh"
 
@@ -335,17 +336,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
 // ---------------------------------------------------------------------------------------------------------------
 // fused edge kernel
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA per SM, persistent over a contiguous range of 128-row tiles.  A tile = up to EDGE_MAXG target atoms i of
-// one molecule x all their neighbours j != i (rows ordered i-major, j ascending).
+// One CTA per SM, persistent over a contiguous range of tiles.  A tile = up to 128 consecutive rows of a molecule's
+// target-major edge list (target i, then its neighbours j != i ascending), touching at most EDGE_MAXG targets; see
+// EdgeTile below for how a target whose neighbour list is cut by a tile boundary is completed.
 //
-//   warp 0      bulk-copy producer: per tile P rows (ng) + Q rows (molecule change only), per K chunk two 28 KB
-//               half-blocks of W2 into a 3-slot ring
-//   warp 1      tcgen05.mma issuer, TS mode: A operand read from TMEM, B (W2) from shared memory, D in TMEM
-//   warps 2-17  compute: 4 threads per tile row (= TMEM lane).  A generation writes SiLU(P_i+Q_j+d2*wc+d02*wd)
-//               straight into a 2-stage A ring in TMEM (columns 448..511) with tcgen05.st -- the A operand never
-//               touches shared memory, which is the bandwidth-critical resource of this kernel (the SS-mode version
-//               spent ~200 KB of shared-memory traffic per K chunk and ran at the 128 B/clk crossbar limit).
-//               Epilogue: pass 1 SiLU + gate dot (thread-local per row), pass 2 gate + segment sum over j.
+//   warp 0      bulk-copy producer: per tile the P rows of its targets + the molecule's Q rows (on a molecule change),
+//               per K chunk the W2 block (pair mode: this CTA's 2 x 112 rows of it) into a 3-slot ring
+//   warp 1      tcgen05.mma issuer, TS mode: A operand read from TMEM, B (W2) from shared memory, D in TMEM columns
+//               0..447.  Pair mode (default): the leader CTA issues cta_group::2 MMAs with M = 256 for both CTAs' tiles,
+//               the peer's warp 1 relays "my half of the W2 slot has landed".
+//   warps 2-17  compute: 4 threads per tile row (= TMEM lane), each owning a quarter of the K / N range.
+//     A generation  SiLU(P_i+Q_j+d2*wc+d02*wd) goes straight into a 2-stage A ring in TMEM (columns 448..511) with
+//                   tcgen05.st -- the A operand never touches shared memory, which is the bandwidth-critical resource of
+//                   this kernel (the SS-mode version spent ~200 KB of shared-memory traffic per K chunk and ran at the
+//                   128 B/clk crossbar limit).  bf16 mode: packed bf16x2 arithmetic throughout.
+//     pass 1        SiLU of the accumulator + dot with the gate / coordinate vector (thread-local per row); bf16 GCL also
+//                   stages the messages in shared memory as the A operand of the segment-sum MMAs.
+//     pass 2        GCL: gate, neighbour sum (bf16: on the tensor core with the gate folded into the selector; tf32: fp32
+//                   shared-memory reader), output in operand format.  Equivariant layer: coordinate update.
+//                   bf16: the first two A chunks of the NEXT tile are generated here, while the tensor core / the other
+//                   warps finish this tile.
 // The per-layer vectors wc, wd, wv live in the constant bank (kernel parameters): warp-uniform operands that cost no
 // shared-memory bandwidth.
 constexpr int EDGE_MAXG = 12;          // max target nodes (groups) per 128-row tile
@@ -364,7 +374,8 @@ constexpr int EDGE_CT = 512;           // compute threads (16 warps)
 constexpr int EDGE_THREADS = 64 + EDGE_CT;  // warp 0 producer, warp 1 MMA, warps 2..17 compute
 
 // Shared-memory layout.  bf16 mode stores the P/Q projections as bf16 (no accuracy cost: emulated and measured) which
-// halves the A-generation loads and leaves room for a second segment-sum staging buffer.
+// halves the A-generation loads and leaves room for two of the four segment-sum staging blocks (the other two borrow the
+// W ring).  The second half of the selector area holds the carried partial sums of split targets.
 template <int kMode>
 struct EdgeSmemT {
   static constexpr bool BF = (kMode == PREC_BF16);
