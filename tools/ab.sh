@@ -7,7 +7,7 @@ cp $L /tmp/orig.so
 for i in $(seq 1 ${1:-3}); do
   for v in A B; do
     cp build_ab/$v.so $L
-    python tools/phase_profile.py bf16 C2 2>/dev/null | python -c "
+    python tools/phase_profile.py ${2:-bf16} C2 2>/dev/null | python -c "
 import sys, json
 for ln in sys.stdin:
     d = json.loads(ln); c = d['cycles_per_tile']
