@@ -182,6 +182,13 @@ float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, void* stream);
  * segment-sum MMA, TMEM load + gate + pack, stage + arrive, readout).  out must hold 16 doubles.  Synchronous. */
 int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, void* stream);
 
+/* Diagnostics: cycle counters of one node-GEMM launch on the current batch, averaged over CTAs.  which: 0 = P/Q projection
+ * of layer 0, 1 = first node-MLP GEMM (SiLU epilogue), 2 = second node-MLP GEMM (residual epilogue; adds a second copy of
+ * the update to the residual stream -- call it on a scratch state only).  out[0] producer waits for a free ring slot,
+ * [1] MMA issuer waits for operands, [2] MMA issuer waits for the epilogue, [3] epilogue waits for the accumulator,
+ * [4] epilogue proper, [5] tiles per CTA, [6] CTA lifetime (all but [5] in cycles per CTA), [7] launch ms.  Synchronous. */
+int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, void* stream);
+
 /* Test hook: C[M x N] = A[M x K] . W[N x K]^T + bias through the tcgen05 GEMM kernel (row-major fp32 in / out,
  * converted to operand format internally).  mode = MLCG_PREC_TF32 or MLCG_PREC_BF16; bn = 448 or 256. */
 int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,

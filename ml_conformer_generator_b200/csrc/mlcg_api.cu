@@ -1269,6 +1269,59 @@ extern "C" int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_r
   return MLCG_OK;
 }
 
+extern "C" int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, void* stream) {
+  if (!h || !out) return MLCG_E_ARG;
+  if (!h->egnn_loaded || !h->batch_set || h->precision == PREC_FP32_SIMT || which < 0 || which > 2)
+    FAIL(MLCG_E_STATE, "gemm_phase_profile: needs a tensor-core precision, weights, a batch and which in 0..2");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int mode = h->precision, kc = h->kc448();
+  const LayerW& L = h->layers[0];
+  const int grid = std::min(h->n_mtiles * (which == 0 ? 2 : 1), h->num_sms);
+  DevBuf buf;
+  CK(buf.ensure((size_t)grid * 8 * sizeof(long long)));
+  CK(cudaMemsetAsync(buf.p, 0, (size_t)grid * 8 * sizeof(long long), st));
+  GemmArgs a{};
+  a.prof = buf.as<long long>();
+  a.m_rows = h->M;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  if (which == 0) {
+    a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
+    a.w = L.w1ab_op.as<uint8_t>(); a.bias = L.bias_pq.as<float>();
+    a.out_f32 = h->pq.as<float>(); a.ldo = 2 * HP; a.n_valid = 2 * HP;
+    if (mode == PREC_BF16) CK((launch_gemm<PREC_BF16, HP, EPI_BF16>(a, h->n_mtiles, 2, st)));
+    else CK((launch_gemm<PREC_TF32, HP, EPI_F32>(a, h->n_mtiles, 2, st)));
+  } else if (which == 1) {
+    a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc;
+    a.a1 = h->agg_op.as<uint8_t>(); a.a1_per_tile = kc; a.n_kc = 2 * kc;
+    a.w = L.w3_op.as<uint8_t>(); a.bias = L.b3p.as<float>();
+    a.out_op = h->t_op.as<uint8_t>(); a.out_op_chunks = kc;
+    CK((launch_gemm_mode<HP, EPI_SILU_OP>(mode, a, h->n_mtiles, 1, st)));
+  } else {
+    a.a0 = h->t_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
+    a.w = L.w4_op.as<uint8_t>(); a.bias = L.b4p.as<float>();
+    a.out_op = h->h_op.as<uint8_t>(); a.out_op_chunks = kc; a.resid = h->h_res.as<float>(); a.ldr = 0;
+    CK((launch_gemm_mode<HP, EPI_RESID_OP>(mode, a, h->n_mtiles, 1, st)));
+  }
+  CK(cudaEventRecord(e1, st));
+  h->launches++;
+  std::vector<long long> host((size_t)grid * 8);
+  CK(cudaMemcpyAsync(host.data(), buf.p, host.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  buf.release();
+  for (int k = 0; k < 8; ++k) out[k] = 0.0;
+  for (int b = 0; b < grid; ++b)
+    for (int k = 0; k < 7; ++k) out[k] += (double)host[(size_t)b * 8 + k] / grid;
+  out[7] = ms;
+  return MLCG_OK;
+}
+
 extern "C" int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,
                               int M, int N, int K, void* stream) {
   if (!h) return MLCG_E_ARG;

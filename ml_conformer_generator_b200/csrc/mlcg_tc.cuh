@@ -41,6 +41,9 @@ struct GemmArgs {
   float* resid;           // EPI_RESID_OP: fp32 residual stream, updated in place
   int ldr;
   int n_mtiles, n_ntiles; // tile grid (set by the launcher); the kernel is persistent and walks it with stride gridDim.x
+  long long* prof;        // optional [grid][8] cycle counters (diagnostics): 0 producer waits for a free slot, 1 MMA issuer
+                          // waits for operands, 2 MMA issuer waits for the epilogue, 3 epilogue waits for the accumulator,
+                          // 4 epilogue proper, 5 tiles, 6 CTA lifetime
 };
 
 template <int BN>
@@ -104,16 +107,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
 #pragma unroll
       for (int s = 0; s < Cfg::NSTAGE; ++s) uses[s] = 0;
       int tl = 0;
+      long long w_slot = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
         for (int kc = 0; kc < p.n_kc; ++kc) {
           const int sl = (kc + 1) % Cfg::NSTAGE;
+          const long long c0 = p.prof ? clock64() : 0;
           if (tl > 0 && kc == Cfg::NSTAGE - 1) mbar_wait(epi_done, (uint32_t)((tl - 1) & 1));  // staging (slot 0) is free again
           uint32_t u = 0;
 #pragma unroll
           for (int s = 0; s < Cfg::NSTAGE; ++s)
             if (s == sl) { u = uses[s]; uses[s]++; }
           mbar_wait(empty_bar(sl), (u & 1u) ^ 1u);
+          if (p.prof) w_slot += clock64() - c0;
           mbar_arrive_expect_tx(full_bar(sl), Cfg::STAGE_BYTES);
           const uint8_t* asrc = (kc < p.a0_chunks)
                                     ? p.a0 + ((size_t)mt * p.a0_per_tile + kc) * A_CHUNK_BYTES
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
           bulk_g2s(sa + A_CHUNK_BYTES, wsrc, BN * CHUNK_BYTES, full_bar(sl));
         }
       }
+      if (p.prof) p.prof[(size_t)blockIdx.x * 8 + 0] = w_slot;
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -132,10 +139,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
 #pragma unroll
       for (int s = 0; s < Cfg::NSTAGE; ++s) uses[s] = 0;
       int tl = 0;
+      long long w_ops = 0, w_epi = 0;
+      const long long t_start = p.prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
         if (tl > 0) {  // the previous tile's accumulator has been read out
+          const long long c0 = p.prof ? clock64() : 0;
           mbar_wait(epi_done, (uint32_t)((tl - 1) & 1));
           tc_fence_after();
+          if (p.prof) w_epi += clock64() - c0;
         }
         for (int kc = 0; kc < p.n_kc; ++kc) {
           const int sl = (kc + 1) % Cfg::NSTAGE;
@@ -143,8 +154,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
 #pragma unroll
           for (int s = 0; s < Cfg::NSTAGE; ++s)
             if (s == sl) { u = uses[s]; uses[s]++; }
+          const long long c1 = p.prof ? clock64() : 0;
           mbar_wait(full_bar(sl), u & 1u);
           tc_fence_after();
+          if (p.prof) w_ops += clock64() - c1;
           const uint32_t sa = base + sl * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc_sw128(sa);
 #pragma unroll
@@ -158,9 +171,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         }
         umma_commit(dfull_bar);
       }
+      if (p.prof) {
+        p.prof[(size_t)blockIdx.x * 8 + 1] = w_ops;
+        p.prof[(size_t)blockIdx.x * 8 + 2] = w_epi;
+        p.prof[(size_t)blockIdx.x * 8 + 5] = tl;
+        p.prof[(size_t)blockIdx.x * 8 + 6] = clock64() - t_start;
+      }
     }
   } else {
    int tl = 0;
+   long long w_acc = 0, t_epi = 0;
    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
     const int mt = tile / p.n_ntiles, nt = tile - mt * p.n_ntiles;
     // bias of this tile's columns -> shared memory while the main loop runs (a global load inside the column loop would
@@ -173,8 +193,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
     const int row = q * 32 + lane;
     const int grow = mt * TILE_M + row;
     const bool rvalid = grow < p.m_rows;
+    const long long pc0 = p.prof ? clock64() : 0;
     mbar_wait(dfull_bar, (uint32_t)(tl & 1));
     tc_fence_after();
+    const long long pc1 = p.prof ? clock64() : 0;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     if constexpr (kEpi == EPI_F32) {
       float rs = 1.0f;
@@ -326,6 +348,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(epi_done);
+    if (p.prof) { w_acc += pc1 - pc0; t_epi += clock64() - pc1; }
+   }
+   if (p.prof && warp == 2 && lane == 0) {
+     p.prof[(size_t)blockIdx.x * 8 + 3] = w_acc;
+     p.prof[(size_t)blockIdx.x * 8 + 4] = t_epi;
    }
   }
   tc_fence_before();

@@ -220,6 +220,15 @@ class Engine:
                  "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout", "a_handoff"]
         return {n: float(out[i]) for i, n in enumerate(names)}
 
+    def gemm_phase_profile(self, which: int) -> dict:
+        """Cycle counters of one node-GEMM launch (0 = P/Q projection, 1 = SiLU GEMM, 2 = residual GEMM) on the current
+        batch; see mlcg_gemm_phase_profile.  Diagnostics only (which = 2 modifies the residual stream)."""
+        out = (C.c_double * 8)()
+        self._check(self.lib.mlcg_gemm_phase_profile(self.h, which, out, self._stream()), "gemm_phase_profile")
+        names = ["producer_wait_slot", "mma_wait_operands", "mma_wait_epilogue", "epi_wait_accumulator", "epilogue",
+                 "tiles_per_cta", "cta_lifetime", "launch_ms"]
+        return {n: float(out[i]) for i, n in enumerate(names)}
+
     def test_gemm(self, mode: str, bn: int, a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
         a = a.to(self.device, torch.float32).contiguous()
         w = w.to(self.device, torch.float32).contiguous()

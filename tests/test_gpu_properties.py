@@ -150,3 +150,17 @@ def test_shape_self_similarity_and_batch_invariance(engines):
     padded[1, :coords.size(1)] = coords[1]
     part = sc.evaluate(ref, padded, n[[3, 1]])["scores"]
     assert torch.equal(part[0], full[3]) and torch.equal(part[1], full[1])
+
+
+def test_gemm_phase_profile_is_consistent(engines):
+    """The diagnostic counters of the node GEMMs add up: an epilogue warp's waiting + working time and the MMA issuer's
+    lifetime describe the same CTA, and every CTA processed its share of the tiles."""
+    e = engines("bf16")
+    n_nodes, nm, z, ctx, t = _batch(64, 5)
+    e.set_batch(n_nodes.numpy(), 39)
+    e.egnn_forward(t, z, ctx)
+    for which in (0, 1):
+        p = e.gemm_phase_profile(which)
+        assert p["tiles_per_cta"] > 0.999 and p["launch_ms"] > 0
+        assert p["cta_lifetime"] > 0 and p["epilogue"] > 0
+        assert p["epi_wait_accumulator"] + p["epilogue"] < 1.5 * p["cta_lifetime"] + 5000
