@@ -168,6 +168,15 @@ int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_ref, const f
                         int N, const float* frames, const float* orient, int n_orient, const float* axes, int G,
                         float amplitude, float atom_radius, float* workspace, float* scores, float* aligned, void* stream);
 
+/* Host-only (no device, no handle): the plan of the fused edge kernel for a batch.  tiles_out receives 8 int32 per tile
+ * {molecule, rows of the first target that precede the tile, rows, atoms, first target, targets touched, state of the
+ * first target, state of the last target} with state -1 = whole, -2 = carried in shared memory between two consecutive
+ * tiles of one CTA, >= 0 = side-buffer id (cut between two CTAs); owner_out the CTA (of min(tiles, num_sms) CTAs, paired
+ * as the kernel pairs them) that processes each tile; *n_fix_out the number of side-buffer targets.  Returns the number
+ * of tiles (at most max_tiles entries are written) or a negative error code. */
+int mlcg_plan_edge_tiles(const int32_t* n_nodes_host, int B, int N, int num_sms, int32_t* tiles_out, int32_t* owner_out,
+                         int max_tiles, int32_t* n_fix_out);
+
 /* Introspection for benches / tests. */
 int mlcg_num_edge_tiles(mlcg_handle* h);
 int64_t mlcg_num_edges(mlcg_handle* h);          /* sum_b n_b (n_b - 1) */

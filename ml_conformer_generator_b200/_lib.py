@@ -17,7 +17,7 @@ EXPORTS = [
     "mlcg_set_batch", "mlcg_egnn_forward", "mlcg_noise_init", "mlcg_step", "mlcg_reinject", "mlcg_forward_diffuse",
     "mlcg_decode", "mlcg_sample", "mlcg_seer_inputs", "mlcg_seer_forward", "mlcg_generate", "mlcg_num_edge_tiles",
     "mlcg_num_edges", "mlcg_kernel_launches", "mlcg_time_edge_kernel", "mlcg_edge_phase_profile", "mlcg_test_gemm",
-    "mlcg_shape_moments", "mlcg_shape_tanimoto", "mlcg_gemm_phase_profile",
+    "mlcg_shape_moments", "mlcg_shape_tanimoto", "mlcg_gemm_phase_profile", "mlcg_plan_edge_tiles",
 ]
 
 
@@ -94,6 +94,7 @@ def load() -> C.CDLL:
     lib.mlcg_edge_phase_profile.argtypes = [vp, ci, C.POINTER(C.c_double), vp]
     lib.mlcg_test_gemm.argtypes = [vp, ci, ci, vp, vp, vp, vp, ci, ci, ci, vp]
     lib.mlcg_gemm_phase_profile.argtypes = [vp, ci, C.POINTER(C.c_double), vp]
+    lib.mlcg_plan_edge_tiles.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp]
     lib.mlcg_shape_moments.argtypes = [vp, vp, vp, ci, ci, C.c_float, C.c_float, ci, vp, vp]
     lib.mlcg_shape_tanimoto.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp, vp, ci, vp, ci, C.c_float, C.c_float, vp, vp, vp, vp]
     _lib = lib

@@ -209,9 +209,9 @@ static int edge_grid_for(int n_tiles, int num_sms) {
   return g;
 }
 // which CTA processes tile t: the same contiguous ranges k_tc_edge computes from (blockIdx, gridDim, n_tiles)
-static void edge_tile_owner(mlcg_handle* h, int n_tiles, std::vector<int>& owner) {
+static void edge_tile_owner(int num_sms, int n_tiles, std::vector<int>& owner) {
   owner.assign(n_tiles, 0);
-  int grid = edge_grid_for(n_tiles, h->num_sms);
+  int grid = edge_grid_for(n_tiles, num_sms);
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
   if (grid <= 0) return;
@@ -507,6 +507,74 @@ extern "C" int mlcg_load_seer(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
 // ---------------------------------------------------------------------------------------------------------------
 // batch plan
 // ---------------------------------------------------------------------------------------------------------------
+// Host-only plan of the fused edge kernel for a batch: the tile table (section 4.1 of DESIGN.md) and the targets that go
+// through the side buffer.  Pure function of (atom counts, SM count, environment switches); also exported for tests.
+static int plan_edge_tiles(const int32_t* n_nodes, int B, int N, int num_sms, std::vector<EdgeTile>& tiles,
+                           std::vector<int>& fix_node, std::vector<int>& node_off, std::string& err) {
+  tiles.clear();
+  fix_node.clear();
+  node_off.assign(B + 1, 0);
+  for (int b = 0; b < B; ++b) {
+    const int n = n_nodes[b];
+    if (n < 1 || n > N) { err = "set_batch: n_nodes[b] must be in [1, N]"; return MLCG_E_ARG; }
+    node_off[b + 1] = node_off[b] + n;
+    const int nm1 = n - 1, node0 = node_off[b];
+    if (nm1 < EDGE_MAXG || !edge_split_mode()) {
+      // few neighbours per target: whole targets per tile (a 128-row window could touch more than EDGE_MAXG targets)
+      const int gmax = std::min(EDGE_MAXG, n > 1 ? TILE_M / nm1 : EDGE_MAXG);
+      for (int i0 = 0; i0 < n; i0 += gmax) {
+        const int ng = std::min(gmax, n - i0);
+        tiles.push_back(EdgeTile{b, 0, ng * nm1, n, i0, ng, EDGE_WHOLE, EDGE_WHOLE});
+      }
+    } else {
+      // cut the n(n-1) target-major edge rows into near-equal ranges of at most 128 rows
+      const int E = n * nm1, T = (E + TILE_M - 1) / TILE_M;
+      for (int k = 0; k < T; ++k) {
+        const int ra = (int)((long long)k * E / T), rb = (int)((long long)(k + 1) * E / T);
+        const int i_first = ra / nm1, i_last = (rb - 1) / nm1;
+        // provisional: fixb = node whose neighbour list is cut at the end of this tile (resolved below)
+        tiles.push_back(EdgeTile{b, ra - i_first * nm1, rb - ra, n, i_first, i_last - i_first + 1, EDGE_WHOLE,
+                                 (rb % nm1 != 0) ? node0 + i_last : EDGE_WHOLE});
+      }
+    }
+  }
+  // Resolve the split targets.  The edge kernel gives every CTA a contiguous tile range (edge_tile_owner mirrors it): a
+  // target cut between two tiles of one CTA is carried in shared memory, one cut between two CTAs goes through the
+  // side buffer + k_edge_fixup.
+  std::vector<int> owner;
+  edge_tile_owner(num_sms, (int)tiles.size(), owner);
+  for (size_t t = 0; t + 1 < tiles.size(); ++t) {
+    if (tiles[t].fixb == EDGE_WHOLE) continue;
+    const int node = tiles[t].fixb;
+    if (owner[t] == owner[t + 1]) {
+      tiles[t].fixb = tiles[t + 1].fixa = EDGE_CARRY;
+    } else {
+      tiles[t].fixb = tiles[t + 1].fixa = (int)fix_node.size();
+      fix_node.push_back(node);
+    }
+  }
+  return MLCG_OK;
+}
+
+/* Test / introspection hook (no device needed): the edge-tile plan for a batch as 8 ints per tile (EdgeTile) and the
+ * CTA that owns each tile.  Returns the number of tiles (or < 0); fills at most max_tiles entries. */
+extern "C" int mlcg_plan_edge_tiles(const int32_t* n_nodes, int B, int N, int num_sms, int32_t* tiles_out, int32_t* owner_out,
+                                    int max_tiles, int32_t* n_fix_out) {
+  if (!n_nodes || B <= 0 || N <= 0 || N > EDGE_MAXN || num_sms <= 0) return MLCG_E_ARG;
+  std::vector<EdgeTile> tiles;
+  std::vector<int> fix_node, node_off, owner;
+  std::string err;
+  const int rc = plan_edge_tiles(n_nodes, B, N, num_sms, tiles, fix_node, node_off, err);
+  if (rc) return rc;
+  edge_tile_owner(num_sms, (int)tiles.size(), owner);
+  for (int t = 0; t < (int)tiles.size() && t < max_tiles; ++t) {
+    if (tiles_out) memcpy(tiles_out + 8 * t, &tiles[t], sizeof(EdgeTile));
+    if (owner_out) owner_out[t] = owner[t];
+  }
+  if (n_fix_out) *n_fix_out = (int)fix_node.size();
+  return (int)tiles.size();
+}
+
 extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int N) {
   if (!h) return MLCG_E_ARG;
   if (!n_nodes || B <= 0 || N <= 0 || N > EDGE_MAXN) FAIL(MLCG_E_ARG, "set_batch: need B > 0 and 1 <= N <= 39");
@@ -523,30 +591,14 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   std::vector<int> node_mol, node_edge_off;
   std::vector<EdgeTile> tiles;
   std::vector<int> fix_node;
+  {
+    std::string perr;
+    const int prc = plan_edge_tiles(n_nodes, B, N, h->num_sms, tiles, fix_node, h->h_node_off, perr);
+    if (prc) FAIL(prc, perr.c_str());
+  }
   long long edges = 0;
   for (int b = 0; b < B; ++b) {
     const int n = n_nodes[b];
-    if (n < 1 || n > N) FAIL(MLCG_E_ARG, "set_batch: n_nodes[b] must be in [1, N]");
-    h->h_node_off[b + 1] = h->h_node_off[b] + n;
-    const int nm1 = n - 1, node0 = h->h_node_off[b];
-    if (nm1 < EDGE_MAXG || !edge_split_mode()) {
-      // few neighbours per target: whole targets per tile (a 128-row window could touch more than EDGE_MAXG targets)
-      const int gmax = std::min(EDGE_MAXG, n > 1 ? TILE_M / nm1 : EDGE_MAXG);
-      for (int i0 = 0; i0 < n; i0 += gmax) {
-        const int ng = std::min(gmax, n - i0);
-        tiles.push_back(EdgeTile{b, 0, ng * nm1, n, i0, ng, -1, -1});
-      }
-    } else {
-      // cut the n(n-1) target-major edge rows into near-equal ranges of at most 128 rows
-      const int E = n * nm1, T = (E + TILE_M - 1) / TILE_M;
-      for (int k = 0; k < T; ++k) {
-        const int ra = (int)((long long)k * E / T), rb = (int)((long long)(k + 1) * E / T);
-        const int i_first = ra / nm1, i_last = (rb - 1) / nm1;
-        // provisional: fixb = node whose neighbour list is cut at the end of this tile (resolved below)
-        tiles.push_back(EdgeTile{b, ra - i_first * nm1, rb - ra, n, i_first, i_last - i_first + 1, EDGE_WHOLE,
-                                 (rb % nm1 != 0) ? node0 + i_last : EDGE_WHOLE});
-      }
-    }
     for (int i = 0; i < n; ++i) {
       node_mol.push_back(b);
       if (edges + (long long)i * (n - 1) > 0x7fffffffLL) FAIL(MLCG_E_ARG, "set_batch: too many edges for one batch");
@@ -555,23 +607,6 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
     edges += (long long)n * (n - 1);
   }
   h->n_etiles = (int)tiles.size();
-  {
-    // Resolve the split targets.  The edge kernel gives every CTA a contiguous tile range (edge_tile_owner mirrors it): a
-    // target cut between two tiles of one CTA is carried in shared memory, one cut between two CTAs goes through the
-    // side buffer + k_edge_fixup.
-    std::vector<int> owner;
-    edge_tile_owner(h, (int)tiles.size(), owner);
-    for (size_t t = 0; t + 1 < tiles.size(); ++t) {
-      if (tiles[t].fixb == EDGE_WHOLE) continue;
-      const int node = tiles[t].fixb;
-      if (owner[t] == owner[t + 1]) {
-        tiles[t].fixb = tiles[t + 1].fixa = EDGE_CARRY;
-      } else {
-        tiles[t].fixb = tiles[t + 1].fixa = (int)fix_node.size();
-        fix_node.push_back(node);
-      }
-    }
-  }
   h->n_edges = edges;
   h->M = h->h_node_off[B];
   h->n_mtiles = (h->M + TILE_M - 1) / TILE_M;
