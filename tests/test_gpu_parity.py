@@ -104,6 +104,49 @@ def test_teacher_forced_bf16_fp32_distance_terms():
     assert worst < 1e-2
 
 
+_VARIANT_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from conftest import rel_l2
+from ml_conformer_generator_b200.engine import Engine
+from ml_conformer_generator_b200.weights import random_state_dicts
+from oracle import edm_oracle as O
+edm_sd, _ = random_state_dicts(0)
+g = torch.Generator().manual_seed(5)
+n_nodes = torch.cat([torch.arange(1, 40), torch.tensor([39] * 9)])
+B, N = n_nodes.numel(), 39
+nm, _ = O.prepare_masks(n_nodes, N)
+z = torch.randn(B, N, 11, generator=g) * nm
+z[:, :, :3] *= 1.5
+ctx = torch.zeros(B, 3)
+t = torch.full((B,), 0.3)
+out = {}
+for m in ("fp32", "tf32", "bf16"):
+    e = Engine(torch.device("cuda:0"), m); e.load_edm_state_dict(edm_sd)
+    e.set_batch(n_nodes.numpy(), N)
+    out[m] = e.egnn_forward(t, z, ctx).cpu()
+print("ERR", rel_l2(out["tf32"], out["fp32"]), rel_l2(out["bf16"], out["fp32"]))
+"""
+
+
+@pytest.mark.parametrize("env", [{"MLCG_EDGE_PAIR": "0"}, {"MLCG_EDGE_SPLIT": "0"}, {"MLCG_EDGE_GRID": "37"},
+                                 {"MLCG_EDGE_PAIR": "0", "MLCG_EDGE_SPLIT": "0", "MLCG_EDGE_GRID": "5"}])
+def test_kernel_variants_selected_by_environment(env):
+    """The documented runtime switches select other variants of the same CUDA path: single-CTA edge kernel,
+    whole-target tiles, smaller grids (different CTA tile ranges, hence different carried / side-buffer split targets).
+    Each must match the exact fp32 CUDA path on a batch of every size 1..39 (read once per process => subprocess)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root], env=dict(os.environ, **env), capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    tf32_err, bf16_err = (float(v) for v in [ln for ln in out.stdout.splitlines() if ln.startswith("ERR")][-1].split()[1:])
+    print(env, "tf32 vs fp32", tf32_err, "bf16 vs fp32", bf16_err)
+    assert tf32_err < 1e-3 and bf16_err < 2e-2
+
+
 def _tape(g, B):
     return O.NoiseTape.draw(int(g["n_pairs"]), B, int(g["n_max"]), int(g["seed"])).stacked()
 
