@@ -989,6 +989,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // runs 2cb, 2cb+1 of every quarter (32 channels x 4 quarters = 128 MMA rows, row m = 32*qq + c); block 3 holds
           // run 6 of every quarter (16 channels x 4 = 64 rows, m = 16*qq + c).  Layout per block: two 16 KB operand
           // chunks of [128 tile rows x 64 channels], i.e. MN-major A with M = channels, K = tile rows.
+          // Blocks 2 and 3 live in the W ring.  The warps of columns 0..223 started on d_half, i.e. possibly while the last
+          // chunk's MMAs for columns 224..447 were still reading their W slot: they must see d_full before the first store
+          // into the ring (long complete by then; this only makes the ordering explicit).
+          if (ch == 4 && qq < 2) mbar_wait(d_full, (uint32_t)(it & 1));
           uint8_t* dst;
           int piece;
           if (ch < 6) {
