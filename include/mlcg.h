@@ -188,7 +188,8 @@ float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, void* stream);
 /* Diagnostics: mean cycles per 128-row tile spent in each phase of the fused edge kernel for `layer` on the current
  * batch: out[0] row-info + P/Q wait, [1] A generation, [2] MMA tail, [3] epilogue pass 1, [4] pass 2 / coordinate
  * update, [5] A-ring back-pressure (part of [1]), [6] tiles profiled, [7..10] pass-2 sub-phases (wait for the
- * segment-sum MMA, TMEM load + gate + pack, stage + arrive, readout).  out must hold 16 doubles.  Synchronous. */
+ * segment-sum MMAs incl. the next tile's early A generation, unused, selector + publish, readout), [11] A-operand
+ * hand-off (tcgen05.st + publish, part of [1]).  out must hold 16 doubles.  Synchronous. */
 int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, void* stream);
 
 /* Diagnostics: cycle counters of one node-GEMM launch on the current batch, averaged over CTAs.  which: 0 = P/Q projection
