@@ -115,3 +115,24 @@ def test_sdf_blocks_round_trip():
     bo = M.bond_orders_from_logits(logits)
     assert int(bo[0, 1, 0]) == 2 and int(bo.sum()) == 2
 
+
+
+def test_shape_host_helpers_match_oracle():
+    """Host-side pieces of the GPU shape scorer (grid axes incl. the reference's per-atom min/max quirk, orientation
+    matrices, alpha) against the oracle restatement of shape_similarity.py -- no device needed."""
+    from oracle import shape_oracle as S
+    import importlib
+    H = importlib.import_module("ml_conformer_generator_b200.shape_similarity")
+    g = golden("shape")
+    ref_pts = torch.from_numpy(g["ref_pts"])
+    cand = torch.from_numpy(g["pts"][0, : int(g["n_nodes"][0])])
+    ax = H.grid_axes(ref_pts)
+    for k, a in enumerate(S.grid_axes(ref_pts, cand)):
+        assert torch.equal(ax[k], a)
+    assert abs(H.get_alpha() - S.ALPHA) < 1e-15
+    mats = H.orientation_matrices()
+    assert torch.equal(mats[0], torch.eye(3))
+    for k, ang in enumerate(S.orientations()[1:]):
+        assert torch.equal(cand @ mats[k + 1], S.rotate(cand, ang)) or torch.allclose(cand @ mats[k + 1], S.rotate(cand, ang), atol=1e-6)
+    with pytest.raises(ValueError):
+        H.grid_axes(ref_pts[:2])
