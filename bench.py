@@ -2,7 +2,7 @@
 """Headline benchmark: generated molecules / second through the hot path (T=100 reverse steps = 101 EGNN forwards,
 then GCN-input build + AdjMatSeer + bond argmax), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|tf32] [--workload C2|C3|C1|C4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|tf32] [--workload C2|C3|C1|C4|C5]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
   python bench.py --impl reference ...        (reference CPU path = oracle port, timed on the host cores)
 
@@ -31,8 +31,20 @@ MAC_PER_EDGE = 420 * 420 + 420 + 2 * 420  # second edge layer + gate/coord head 
 MAC_PER_NODE = 19_061_280                 # per node per forward
 
 
-def workload(name, seed_shift=0):
+def workload(name, seed_shift=0, world=1, rank=0):
     rng = np.random.RandomState(1234 + seed_shift)
+    if name == "C5":
+        # 65 536 samples of 15-39 atoms in total, sharded contiguously over the ranks (strong scaling); every
+        # rank works through its share in sub-batches of 8192.  Sizes are drawn for the GLOBAL sample ids, so the job is the
+        # same whatever the number of ranks.
+        total, chunk = 65536, 8192
+        sizes = np.random.RandomState(5).randint(15, 40, total).astype(np.int32)
+        per = total // world
+        mine = sizes[rank * per:(rank + 1) * per]
+        chunks = [mine[i:i + chunk] for i in range(0, per, chunk)]
+        return dict(B=len(chunks[0]), N=39, n_nodes=chunks[0], chunks=chunks, total=total, per_rank=per, ctx=ONNX_CONTEXT,
+                    desc="C5: 65536 samples of 15-39 atoms in total over %d GPU(s) (strong scaling, sub-batches of %d), "
+                         "T=100 + AdjMatSeer GCN" % (world, len(chunks[0])))
     if name == "C2":
         return dict(B=1024, N=39, n_nodes=np.full(1024, 39, np.int32), ctx=ONNX_CONTEXT,
                     desc="C2: B=1024 samples x 39 atoms, T=100 (101 EGNN forwards) + AdjMatSeer GCN")
@@ -199,7 +211,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -220,8 +232,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    wl = workload(args.workload, seed_shift=rank)
+    wl = workload(args.workload, seed_shift=rank, world=world, rank=rank)
     B, N = wl["B"], wl["N"]
+    chunks = wl.get("chunks")  # strong-scaling workload: this rank's share, processed in sub-batches
     eng = Engine(dev, args.precision)
     sd, ssd = random_state_dicts(0)
     eng.load_edm_state_dict(sd)
@@ -240,9 +253,9 @@ def main():
     zk_dev = torch.from_numpy(wl["z_known"]).to(dev) if mode != "forward" else None
     fm_dev = torch.from_numpy(wl["fixed_mask"]).to(dev) if mode != "forward" else None
 
-    def device_step(seed):
+    def device_batch(seed, offset):
         x, cls = eng.sample(ctx_dev, T_STEPS, mode, wl.get("resample", 0), z_known=zk_dev, fixed_mask=fm_dev, seed=seed,
-                            sample_offset=rank * B)
+                            sample_offset=offset)
         el, dmat, adj = eng.seer_inputs(x, cls)
         _, bonds = eng.seer_forward(el, dmat, adj, want_logits=False)
         if world > 1:  # the single collective of the path: final gather of coordinates / types / bonds
@@ -250,6 +263,14 @@ def main():
             dist.all_gather_into_tensor(gather[1], cls)
             dist.all_gather_into_tensor(gather[2], bonds)
         return x, cls, bonds
+
+    def device_step(seed):
+        if chunks is None:
+            return device_batch(seed, rank * B)
+        for ci, nn in enumerate(chunks):   # the batch plan (edge-tile table) is rebuilt per sub-batch: part of the job
+            eng.set_batch(nn, N)
+            out = device_batch(seed, rank * wl["per_rank"] + ci * B)
+        return out
 
     def sync():
         if world > 1:
@@ -275,12 +296,15 @@ def main():
     # host-buffer entry point covers plain generation, so the fragment workload reports the device-timed value only
     e2e_ms = float("nan")
     if mode == "forward":
-        out = eng.generate_host(wl["n_nodes"], N, ctx_np, T_STEPS, 0, seed=300, sample_offset=rank * B)
+        parts = chunks if chunks is not None else [wl["n_nodes"]]
+        base = rank * (wl["per_rank"] if chunks is not None else B)
+        out = eng.generate_host(parts[0], N, ctx_np, T_STEPS, 0, seed=300, sample_offset=base)
         sync()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = max(1, min(args.steps, 2)) if chunks is None else 1
         for i in range(e2e_steps):
-            eng.generate_host(wl["n_nodes"], N, ctx_np, T_STEPS, 0, seed=400 + i, sample_offset=rank * B, out=out)
+            for ci, nn in enumerate(parts):
+                eng.generate_host(nn, N, ctx_np, T_STEPS, 0, seed=400 + i, sample_offset=base + ci * B, out=out)
         sync()
         e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
 
@@ -297,13 +321,16 @@ def main():
         pk = peaks()
         edge_flops = 2.0 * MAC_PER_EDGE * n_edges
         achieved = edge_flops / (edge_ms * 1e-3) / 1e12
-        step_flops = alg_flops_forward(wl["n_nodes"]) * n_forwards + 1.871e9 * B
+        mine = np.concatenate(chunks) if chunks is not None else wl["n_nodes"]
+        step_flops = alg_flops_forward(mine) * n_forwards + 1.871e9 * len(mine)
+        n_job = wl["total"] if chunks is not None else world * B  # molecules per step over all ranks
         prof = os.path.join(ROOT, "profiles", "edge_kernel_traffic.json")
         traffic = json.load(open(prof)).get(args.precision) if os.path.exists(prof) else None
         res = {
             "metric": "generated mols/sec (100 EGNN steps + GCN, <=39 atoms)",
-            "value": world * B / (ms * 1e-3), "unit": "mols/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "value": n_job / (ms * 1e-3), "unit": "mols/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if chunks is not None else "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": wl["desc"], "per_gpu_batch": B, "max_atoms": N, "diffusion_steps": T_STEPS,
                        "weights": "random-init (seed 0) of the reference architecture",
@@ -311,9 +338,9 @@ def main():
                        "l2": "per-step working set (PQ projections %.0f MB + operands) exceeds the 126 MB L2; no flush"
                              % (eng.n_nodes.sum().item() * 896 * 4 / 1e6),
                        "parallelism": "dp%d, no collective inside the loop, one NCCL all-gather of results" % world},
-            "e2e": ({"value": world * B / (e2e_ms * 1e-3), "unit": "mols/s",
-                     "h2d_bytes_per_step": int(B * 4 + B * 3 * 4),
-                     "d2h_bytes_per_step": int(B * N * 3 * 4 + B * N * 4 + B * 42 * 42)} if e2e_ms == e2e_ms else None),
+            "e2e": ({"value": n_job / (e2e_ms * 1e-3), "unit": "mols/s",
+                     "h2d_bytes_per_step": int(len(mine) * 4 + len(mine) * 3 * 4),
+                     "d2h_bytes_per_step": int(len(mine) * (N * 3 * 4 + N * 4 + 42 * 42))} if e2e_ms == e2e_ms else None),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "k_tc_edge (GCL sub-layer, %s)" % args.precision,
