@@ -53,13 +53,17 @@ typedef struct {
 
 /* Noise source for one draw of sample_combined_position_feature_noise (equivariant_diffusion.py:341-363).
  * raw != NULL : (B, N, 11) raw N(0,1) draws injected by the caller (parity mode; x-part first, then h-part);
- * raw == NULL : device Philox4x32-10 keyed by (seed, sample_offset + b, atom, draw) -- results do not depend on how a
- *               batch is sharded across GPUs. */
+ * raw == NULL : device Philox4x32-10 keyed by (seed, global sample id, atom, draw) -- results do not depend on how a
+ *               batch is sharded across GPUs.  The global id of sample b is sample_ids[b] when sample_ids (a DEVICE
+ *               array of B int64) is given, else sample_offset + b.  key = {seed lo, seed hi}, counter =
+ *               {3*draw + k, atom, id lo, id hi} for k = 0..2: 12 uint32 -> 6 Box-Muller pairs -> 11 normals, so no
+ *               two (sample, atom, draw) triples share a random bit (restated on the host in oracle/philox_oracle.py). */
 typedef struct {
   const float* raw;
   uint64_t seed;
   uint64_t draw;
   int64_t sample_offset;
+  const int64_t* sample_ids;
 } mlcg_noise;
 
 /* Scalars of one reverse step, computed on the host exactly as the reference does in float32 torch
@@ -117,14 +121,15 @@ int mlcg_decode(mlcg_handle* h, const float* z0, const float* eps0, float sigma_
 /* Whole reverse loop on the device.  mode 0 = EquivariantDiffusion.forward (equivariant_diffusion.py:365-421),
  * 1 = .inpaint (:423-513), 2 = .merge_fragments (:515-607).  steps: HOST array of T entries, steps[s] for integer
  * step s (s = T-1 .. 0 are executed; merge skips s > diffusion_level).  ctx: (B,3).  noise_tape: NULL (device
- * Philox, seed) or (n_draws, B, N, 11) raw draws consumed in the reference's order.  z_work: (B,N,11) scratch that
+ * Philox, seed; sample_ids: NULL or a DEVICE array of B global sample ids, see mlcg_noise) or (n_draws, B, N, 11) raw
+ * draws consumed in the reference's order.  z_work: (B,N,11) scratch that
  * holds z_0 on return.  trace_z / trace_eps: optional (n_forwards, B, N, 11) outputs recording every denoiser
  * input / output (parity tests), or NULL. */
 int mlcg_sample(mlcg_handle* h, int mode, int T, const mlcg_step_scalars* steps, int resample_steps,
                 int diffusion_level, float merge_alpha, float merge_sigma, float sigma_0, float alpha_0, float sigma_x,
                 const float* ctx, const float* z_known, const float* fixed_mask, const float* noise_tape,
-                uint64_t seed, int64_t sample_offset, float* z_work, float* x_out, int32_t* atom_class_out,
-                float* trace_z, float* trace_eps, void* stream);
+                uint64_t seed, int64_t sample_offset, const int64_t* sample_ids, float* z_work, float* x_out,
+                int32_t* atom_class_out, float* trace_z, float* trace_eps, void* stream);
 
 /* Replaces (tensor part, declared connectivity rule -- see DESIGN.md): prepare_adj_mat_seer_input
  * (utils/mol_utils.py:159-191).  x: (B,N,3), atom_class: (B,N) -> elements (B,42) int32, dist (B,42,42), adj (B,42,42). */
@@ -136,13 +141,16 @@ int mlcg_seer_inputs(mlcg_handle* h, const float* x, const int32_t* atom_class, 
 int mlcg_seer_forward(mlcg_handle* h, const int32_t* elements, const float* dist, const float* adj, float* logits,
                       int8_t* bonds, int B, void* stream);
 
-/* End-to-end call with HOST buffers (what MLConformerGenerator.generate_tensors uses): uploads n_nodes / context,
- * runs mlcg_set_batch + mlcg_sample(mode 0) + mlcg_seer_inputs + mlcg_seer_forward, downloads results.
- * n_nodes_host (B), ctx_host (B,3) -> x_host (B,N,3), atom_class_host (B,N) int32, bonds_host (B,42,42) int8. */
+/* End-to-end call with HOST inputs (what MLConformerGenerator.generate_tensors and the multi-GPU driver use): uploads
+ * n_nodes / context / sample ids, runs mlcg_set_batch (only when the geometry changed) + mlcg_sample(mode 0) +
+ * mlcg_seer_inputs + mlcg_seer_forward -- replayed as one CUDA graph from the second call with the same geometry on --
+ * and copies the results out.  n_nodes_host (B), ctx_host (B,3), sample_ids_host (B int64 global ids, or NULL =
+ * sample_offset + b) are HOST arrays.  x_out (B,N,3), atom_class_out (B,N) int32, bonds_out (B,42,42) int8 may be
+ * pinned HOST or DEVICE buffers (copied with cudaMemcpyDefault).  Synchronous. */
 int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, const float* ctx_host, int T,
                   const mlcg_step_scalars* steps, int resample_steps, float sigma_0, float alpha_0, float sigma_x,
-                  uint64_t seed, int64_t sample_offset, float* x_host, int32_t* atom_class_host, int8_t* bonds_host,
-                  void* stream);
+                  uint64_t seed, int64_t sample_offset, const int64_t* sample_ids_host, float* x_out,
+                  int32_t* atom_class_out, int8_t* bonds_out, void* stream);
 
 /* ---- Gaussian shape similarity (the tensor part of the reference's evaluate_samples) -------------------------------
  * Replaces get_shape_quadrupole_for_molecule (cheminformatics/shape_similarity.py:18-203: clique enumeration :267-311 and

@@ -26,7 +26,8 @@ class WeightDesc(C.Structure):
 
 
 class Noise(C.Structure):
-    _fields_ = [("raw", C.c_void_p), ("seed", C.c_uint64), ("draw", C.c_uint64), ("sample_offset", C.c_int64)]
+    _fields_ = [("raw", C.c_void_p), ("seed", C.c_uint64), ("draw", C.c_uint64), ("sample_offset", C.c_int64),
+                ("sample_ids", C.c_void_p)]
 
 
 class StepScalars(C.Structure):
@@ -79,11 +80,11 @@ def load() -> C.CDLL:
     lib.mlcg_forward_diffuse.argtypes = [vp, vp, vp, cf, cf, C.POINTER(Noise), vp]
     lib.mlcg_decode.argtypes = [vp, vp, vp, cf, cf, cf, C.POINTER(Noise), vp, vp, vp]
     lib.mlcg_sample.argtypes = [vp, ci, ci, C.POINTER(StepScalars), ci, ci, cf, cf, cf, cf, cf, vp, vp, vp, vp,
-                                C.c_uint64, C.c_int64, vp, vp, vp, vp, vp, vp]
+                                C.c_uint64, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
     lib.mlcg_seer_inputs.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.mlcg_seer_forward.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     lib.mlcg_generate.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(StepScalars), ci, cf, cf, cf, C.c_uint64,
-                                  C.c_int64, vp, vp, vp, vp]
+                                  C.c_int64, vp, vp, vp, vp, vp]
     lib.mlcg_num_edge_tiles.argtypes = [vp]
     lib.mlcg_num_edges.argtypes = [vp]
     lib.mlcg_num_edges.restype = C.c_int64

@@ -85,7 +85,8 @@ struct mlcg_handle {
   // seer workspaces
   DevBuf s_ld, s_la, s_rowd, s_rowa, s_x64, s_y_op, s_x, s_emb, s_add, s_raw, s_y_f32;
   // mlcg_generate device buffers
-  DevBuf g_ctx, g_z, g_x, g_cls, g_el, g_dist, g_adj, g_bonds;
+  DevBuf g_ctx, g_z, g_x, g_cls, g_el, g_dist, g_adj, g_bonds, g_ids;
+  std::vector<int64_t> ids_stage;
   // test gemm
   DevBuf tg_a, tg_w, tg_b, tg_c;
   // CUDA-graph replay of mlcg_generate (whole reverse loop + GCN as one graph)
@@ -284,6 +285,7 @@ static NoiseSrc to_src(const mlcg_handle* h, const mlcg_noise* n) {
   s.seed = n->seed;
   s.draw = n->draw;
   s.sample_offset = n->sample_offset;
+  s.ids = reinterpret_cast<const long long*>(n->sample_ids);
   s.ctl = (h->use_noise_ctl && n->raw == nullptr) ? h->noise_ctl.as<unsigned long long>() : nullptr;
   return s;
 }
@@ -327,7 +329,7 @@ extern "C" void mlcg_destroy(mlcg_handle* h) {
                     &h->h_res, &h->pq, &h->h_op, &h->agg_op, &h->t_op, &h->agg_f32, &h->t_f32, &h->a1, &h->m2, &h->t_dev,
                     &h->eps_dev, &h->s_ld, &h->s_la, &h->s_rowd, &h->s_rowa, &h->s_x64, &h->s_y_op, &h->s_x, &h->s_emb,
                     &h->s_add, &h->s_raw, &h->s_y_f32, &h->g_ctx, &h->g_z, &h->g_x, &h->g_cls, &h->g_el, &h->g_dist,
-                    &h->g_adj, &h->g_bonds, &h->tg_a, &h->tg_w, &h->tg_b, &h->tg_c})
+                    &h->g_adj, &h->g_bonds, &h->g_ids, &h->tg_a, &h->tg_w, &h->tg_b, &h->tg_c})
     b->release();
   delete h;
 }
@@ -338,12 +340,22 @@ extern "C" const char* mlcg_last_error(mlcg_handle* h) { return h ? h->err.c_str
 // weights
 // ---------------------------------------------------------------------------------------------------------------
 static int copy_weights(mlcg_handle* h, const mlcg_weight_desc* w, int n, std::map<std::string, Wt>& dst) {
+  // new weights invalidate a captured generation graph (it holds the old buffers' addresses); nothing may be in flight
+  CK(cudaDeviceSynchronize());
+  if (h->gen_graph) { cudaGraphExecDestroy(h->gen_graph); h->gen_graph = nullptr; }
+  h->gen_key.clear();
+  h->gen_key_hits = 0;
   for (int i = 0; i < n; ++i) {
     if (!w[i].name || !w[i].data || w[i].rows <= 0 || w[i].cols <= 0) FAIL(MLCG_E_ARG, "bad weight descriptor");
     Wt t;
     t.rows = w[i].rows;
     t.cols = w[i].cols;
     const size_t bytes = (size_t)t.rows * t.cols * sizeof(float);
+    auto old = dst.find(w[i].name);
+    if (old != dst.end()) {  // reloading: release the previous copy
+      h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void*)old->second.d), h->owned.end());
+      cudaFree(old->second.d);
+    }
     CK(cudaMalloc((void**)&t.d, bytes));
     h->owned.push_back(t.d);
     CK(cudaMemcpy(t.d, w[i].data, bytes, cudaMemcpyDeviceToDevice));
@@ -579,6 +591,9 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   if (!h) return MLCG_E_ARG;
   if (!n_nodes || B <= 0 || N <= 0 || N > EDGE_MAXN) FAIL(MLCG_E_ARG, "set_batch: need B > 0 and 1 <= N <= 39");
   CK(cudaSetDevice(h->device));
+  // The plan buffers below are rewritten with synchronous copies on the NULL stream while earlier calls may still be
+  // running on the caller's (possibly non-blocking) streams: drain the device first.  set_batch is documented synchronous.
+  CK(cudaDeviceSynchronize());
   // any change of the batch plan invalidates the graph captured by mlcg_generate
   if (h->gen_graph) { cudaGraphExecDestroy(h->gen_graph); h->gen_graph = nullptr; }
   h->gen_key.clear();
@@ -903,8 +918,8 @@ extern "C" int mlcg_decode(mlcg_handle* h, const float* z0, const float* eps0, f
 extern "C" int mlcg_sample(mlcg_handle* h, int mode, int T, const mlcg_step_scalars* steps, int resample_steps,
                            int diffusion_level, float merge_alpha, float merge_sigma, float sigma_0, float alpha_0,
                            float sigma_x, const float* ctx, const float* z_known, const float* fixed_mask,
-                           const float* noise_tape, uint64_t seed, int64_t sample_offset, float* z, float* x_out,
-                           int32_t* atom_class_out, float* trace_z, float* trace_eps, void* stream) {
+                           const float* noise_tape, uint64_t seed, int64_t sample_offset, const int64_t* sample_ids, float* z,
+                           float* x_out, int32_t* atom_class_out, float* trace_z, float* trace_eps, void* stream) {
   STEP_PROLOGUE("sample");
   if (!h->egnn_loaded) FAIL(MLCG_E_STATE, "sample: load the EGNN weights first");
   if (mode < 0 || mode > 2 || T <= 0 || !steps || !ctx || !z || !x_out || !atom_class_out || resample_steps < 0)
@@ -921,6 +936,7 @@ extern "C" int mlcg_sample(mlcg_handle* h, int mode, int T, const mlcg_step_scal
     n.seed = seed;
     n.draw = draw;
     n.sample_offset = sample_offset;
+    n.sample_ids = sample_ids;
     ++draw;
     return n;
   };
@@ -1092,8 +1108,8 @@ extern "C" int mlcg_seer_forward(mlcg_handle* h, const int32_t* elements, const 
 static int generate_device(mlcg_handle* h, int T, const mlcg_step_scalars* steps, int resample_steps, float sigma_0,
                            float alpha_0, float sigma_x, uint64_t seed, int64_t sample_offset, void* stream) {
   int rc = mlcg_sample(h, 0, T, steps, resample_steps, 0, 0.f, 0.f, sigma_0, alpha_0, sigma_x, h->g_ctx.as<float>(), nullptr,
-                       nullptr, nullptr, seed, sample_offset, h->g_z.as<float>(), h->g_x.as<float>(), h->g_cls.as<int32_t>(),
-                       nullptr, nullptr, stream);
+                       nullptr, nullptr, seed, sample_offset, h->g_ids.as<int64_t>(), h->g_z.as<float>(), h->g_x.as<float>(),
+                       h->g_cls.as<int32_t>(), nullptr, nullptr, stream);
   if (rc) return rc;
   if ((rc = mlcg_seer_inputs(h, h->g_x.as<float>(), h->g_cls.as<int32_t>(), h->g_el.as<int32_t>(), h->g_dist.as<float>(),
                              h->g_adj.as<float>(), stream)))
@@ -1104,8 +1120,8 @@ static int generate_device(mlcg_handle* h, int T, const mlcg_step_scalars* steps
 
 extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, const float* ctx_host, int T,
                              const mlcg_step_scalars* steps, int resample_steps, float sigma_0, float alpha_0, float sigma_x,
-                             uint64_t seed, int64_t sample_offset, float* x_host, int32_t* atom_class_host,
-                             int8_t* bonds_host, void* stream) {
+                             uint64_t seed, int64_t sample_offset, const int64_t* sample_ids_host, float* x_host,
+                             int32_t* atom_class_host, int8_t* bonds_host, void* stream) {
   if (!h) return MLCG_E_ARG;
   if (!h->egnn_loaded || !h->seer_loaded) FAIL(MLCG_E_STATE, "generate: load both weight sets first");
   if (!n_nodes_host || !ctx_host || !steps || !x_host || !atom_class_host || !bonds_host) FAIL(MLCG_E_ARG, "generate: null pointer");
@@ -1146,12 +1162,17 @@ extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B,
   CK(h->g_adj.ensure(dd * 4));
   CK(h->g_bonds.ensure(dd));
   CK(h->noise_ctl.ensure(2 * sizeof(unsigned long long)));
+  CK(h->g_ids.ensure((size_t)B * sizeof(int64_t)));
+  // global sample ids (the RNG key): always read from this device buffer, so a captured graph replays with any ids
+  h->ids_stage.resize((size_t)B);
+  for (int b = 0; b < B; ++b) h->ids_stage[b] = sample_ids_host ? sample_ids_host[b] : sample_offset + b;
   static int graphs_enabled = -1;
   if (graphs_enabled < 0) {
     const char* e = getenv("MLCG_GRAPH");
     graphs_enabled = (e == nullptr) ? 1 : (atoi(e) != 0);
   }
   CK(cudaMemcpyAsync(h->g_ctx.p, ctx_host, (size_t)B * 3 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->g_ids.p, h->ids_stage.data(), (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   const unsigned long long ctl[2] = {(unsigned long long)seed, (unsigned long long)sample_offset};
   CK(cudaMemcpyAsync(h->noise_ctl.p, ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
   int rc = MLCG_OK;
@@ -1186,9 +1207,10 @@ extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B,
   }
   h->use_noise_ctl = false;
   if (rc) return rc;
-  CK(cudaMemcpyAsync(x_host, h->g_x.p, bn * 3 * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(atom_class_host, h->g_cls.p, bn * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(bonds_host, h->g_bonds.p, dd, cudaMemcpyDeviceToHost, st));
+  // the outputs may be pinned host buffers or device buffers (multi-GPU driver: results stay on the device for the gather)
+  CK(cudaMemcpyAsync(x_host, h->g_x.p, bn * 3 * 4, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(atom_class_host, h->g_cls.p, bn * 4, cudaMemcpyDefault, st));
+  CK(cudaMemcpyAsync(bonds_host, h->g_bonds.p, dd, cudaMemcpyDefault, st));
   CK(cudaStreamSynchronize(st));
   return MLCG_OK;
 }

@@ -2,8 +2,6 @@
 // packing into operand format, the exact-fp32 SIMT path (precision 0, used as the on-GPU fp32 reference and for
 // debugging), and the AdjMatSeer helper kernels.
 #pragma once
-#include <curand_kernel.h>
-
 #include "mlcg_common.cuh"
 
 namespace mlcg {
@@ -15,10 +13,37 @@ struct NoiseSrc {
   const float* raw;            // [B][N][11] raw N(0,1) draws injected by the host (parity mode) or nullptr
   unsigned long long seed;     // device Philox otherwise: keyed by (seed, global sample id, atom, draw index)
   unsigned long long draw;
-  long long sample_offset;     // global id of sample 0 of this shard (shard-invariant sampling)
+  long long sample_offset;     // global id of sample 0 of this shard when `ids` is null (contiguous shard)
+  const long long* ids;        // optional device array [B] of global sample ids (any sharding reproduces the unsharded run)
   const unsigned long long* ctl;  // optional device pointer to {seed, sample_offset}: overrides the two fields above so a
                                   // captured CUDA graph can be replayed with new seeds
 };
+
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), written out so that the
+// (key, counter) assignment is explicit and can be restated on the host (oracle/philox_oracle.py):
+//   key     = {seed lo, seed hi}
+//   counter = {3 * draw + k, atom, sample id lo, sample id hi},  k = 0, 1, 2  -> 12 uint32 per (sample, atom, draw)
+// Every (sample, atom, draw) owns three counter values of its own, so no two draws share a random bit.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// Box-Muller on two uint32: u = (a + 0.5) / 2^32 in (0, 1], v = (b + 0.5) / 2^32; (r sin 2 pi v, r cos 2 pi v)
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u = fmaf((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float v = fmaf((float)b, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-2.0f * logf(u));
+  float sn, cs;
+  sincospif(2.0f * v, &sn, &cs);
+  return make_float2(r * sn, r * cs);
+}
 
 // Raw draws for atom i of sample b (11 values: 3 position + 8 feature; reference order
 // equivariant_diffusion.py:347-362).
@@ -28,14 +53,19 @@ __device__ __forceinline__ void raw_noise(const NoiseSrc& ns, int b, int i, int 
 #pragma unroll
     for (int c = 0; c < ZC; ++c) out[c] = src[c];
   } else {
-    curandStatePhilox4_32_10_t st;
     const unsigned long long seed = ns.ctl ? ns.ctl[0] : ns.seed;
-    const long long off = ns.ctl ? (long long)ns.ctl[1] : ns.sample_offset;
-    curand_init(seed, (unsigned long long)(off + b) * 64ull + (unsigned long long)i, ns.draw * 3ull, &st);
-    const float4 a = curand_normal4(&st), c = curand_normal4(&st), d = curand_normal4(&st);
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
-    out[4] = c.x; out[5] = c.y; out[6] = c.z; out[7] = c.w;
-    out[8] = d.x; out[9] = d.y; out[10] = d.z;
+    const unsigned long long id = ns.ids ? (unsigned long long)ns.ids[b]
+                                         : (unsigned long long)((ns.ctl ? (long long)ns.ctl[1] : ns.sample_offset) + b);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const uint4 r = philox4x32_10(make_uint4((uint32_t)(3ull * ns.draw + k), (uint32_t)i, (uint32_t)id, (uint32_t)(id >> 32)), key);
+      const float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
+      v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = c.x; v[4 * k + 3] = c.y;
+    }
+#pragma unroll
+    for (int c = 0; c < ZC; ++c) out[c] = v[c];
   }
 }
 

@@ -115,11 +115,19 @@ class Engine:
             arr[s] = _lib.StepScalars(d["t"], d["alpha_ts"], d["c_eps"], d["c_sigma"], d["alpha_s"], d["sigma_s"], blend)
         return gamma, arr
 
+    def _steps_cached(self, T: int, blend_power: int):
+        key = (T, blend_power)
+        cache = self.__dict__.setdefault("_steps_cache", {})
+        if key not in cache:
+            cache[key] = self._steps(T, blend_power)
+        return cache[key]
+
     def sample(self, ctx: torch.Tensor, T: int, mode: str = "forward", resample_steps: int = 0,
                z_known: Optional[torch.Tensor] = None, fixed_mask: Optional[torch.Tensor] = None,
                diffusion_level: int = 50, blend_power: int = 3, noise_tape: Optional[torch.Tensor] = None,
-               seed: int = 0, sample_offset: int = 0, trace: bool = False):
-        """Runs the reverse loop for the batch set by set_batch.  Returns (x (B,N,3), atom_class (B,N) int32[, trace])."""
+               seed: int = 0, sample_offset: int = 0, trace: bool = False, sample_ids=None):
+        """Runs the reverse loop for the batch set by set_batch.  Returns (x (B,N,3), atom_class (B,N) int32[, trace]).
+        Device noise is keyed by (seed, global sample id): `sample_ids` (B int64) or `sample_offset + b`."""
         modes = {"forward": 0, "inpaint": 1, "merge": 2}
         gamma, steps = self._steps(T, blend_power)
         dec = decode_scalars(gamma)
@@ -132,6 +140,11 @@ class Engine:
         zk = None if z_known is None else z_known.to(dev, torch.float32).contiguous()
         fm = None if fixed_mask is None else fixed_mask.to(dev, torch.float32).reshape(B, N).contiguous()
         tape = None if noise_tape is None else noise_tape.to(dev, torch.float32).contiguous()
+        ids = None
+        if sample_ids is not None:
+            ids = torch.as_tensor(np.asarray(sample_ids, dtype=np.int64).reshape(-1)).to(dev).contiguous()
+            if ids.numel() != B:
+                raise ValueError("sample: sample_ids must hold one id per sample")
         r_eff = resample_steps if mode == "forward" else max(resample_steps, 1)
         n_active = T if mode != "merge" else min(diffusion_level, T - 1) + 1
         if mode == "forward":
@@ -149,10 +162,10 @@ class Engine:
         te = torch.empty(n_fwd, B, N, 11, device=dev) if trace else None
         rc = self.lib.mlcg_sample(self.h, modes[mode], T, steps, resample_steps, diffusion_level, lvl["alpha"],
                                   lvl["sigma"], dec["sigma_0"], dec["alpha_0"], dec["sigma_x"], _ptr(ctx), _ptr(zk),
-                                  _ptr(fm), _ptr(tape), seed, sample_offset, _ptr(z), _ptr(x), _ptr(cls), _ptr(tz),
-                                  _ptr(te), self._stream())
+                                  _ptr(fm), _ptr(tape), seed, sample_offset, _ptr(ids), _ptr(z), _ptr(x), _ptr(cls),
+                                  _ptr(tz), _ptr(te), self._stream())
         self._check(rc, "sample")
-        self._keep = [ctx, zk, fm, tape]
+        self._keep = [ctx, zk, fm, tape, ids]
         if trace:
             return x, cls, (tz, te)
         return x, cls
@@ -182,18 +195,31 @@ class Engine:
         return logits, bonds
 
     def generate_host(self, n_nodes: np.ndarray, max_n_nodes: int, ctx: np.ndarray, T: int = 100,
-                      resample_steps: int = 0, seed: int = 0, sample_offset: int = 0, out=None):
-        """End-to-end with host (pinned) buffers: returns (x (B,N,3) f32, atom_class (B,N) i32, bonds (B,42,42) i8)."""
+                      resample_steps: int = 0, seed: int = 0, sample_offset: int = 0, out=None, sample_ids=None,
+                      device_out: bool = False):
+        """End-to-end with host inputs: returns (x (B,N,3) f32, atom_class (B,N) i32, bonds (B,42,42) i8) in pinned host
+        buffers, or -- `device_out=True`, used by the multi-GPU driver whose gather runs on the device -- in device
+        tensors.  `sample_ids` (B int64): global ids keying the device noise (default `sample_offset + b`)."""
         nn = np.ascontiguousarray(np.asarray(n_nodes, dtype=np.int32).reshape(-1))
         B, N = int(nn.size), int(max_n_nodes)
         ctxh = torch.from_numpy(np.ascontiguousarray(ctx, dtype=np.float32).reshape(B, 3)).pin_memory()
+        ids = None
+        if sample_ids is not None:
+            ids = np.ascontiguousarray(np.asarray(sample_ids, dtype=np.int64).reshape(-1))
+            if ids.size != B:
+                raise ValueError("generate_host: sample_ids must hold one id per sample")
         if out is None:
-            out = (torch.empty(B, N, 3).pin_memory(), torch.empty(B, N, dtype=torch.int32).pin_memory(),
-                   torch.empty(B, 42, 42, dtype=torch.int8).pin_memory())
-        gamma, steps = self._steps(T, 3)
+            if device_out:
+                out = (torch.empty(B, N, 3, device=self.device), torch.empty(B, N, dtype=torch.int32, device=self.device),
+                       torch.empty(B, 42, 42, dtype=torch.int8, device=self.device))
+            else:
+                out = (torch.empty(B, N, 3).pin_memory(), torch.empty(B, N, dtype=torch.int32).pin_memory(),
+                       torch.empty(B, 42, 42, dtype=torch.int8).pin_memory())
+        gamma, steps = self._steps_cached(T, 3)
         dec = decode_scalars(gamma)
         rc = self.lib.mlcg_generate(self.h, nn.ctypes.data_as(C.c_void_p), B, N, _ptr(ctxh), T, steps, resample_steps,
-                                    dec["sigma_0"], dec["alpha_0"], dec["sigma_x"], seed, sample_offset, _ptr(out[0]),
+                                    dec["sigma_0"], dec["alpha_0"], dec["sigma_x"], seed, sample_offset,
+                                    None if ids is None else ids.ctypes.data_as(C.c_void_p), _ptr(out[0]),
                                     _ptr(out[1]), _ptr(out[2]), self._stream())
         self._check(rc, "generate")
         self.B, self.N = B, N

@@ -1,12 +1,18 @@
 """Multi-GPU host logic.  Samples are independent through the whole reverse loop and the GCN, so a batch
-is sharded across ranks with NO collective inside the loop; the only exchange is one gather of the results
-(coordinates, atom classes, bond matrices).  One process per GPU; `torch.distributed` (NCCL on GPUs, gloo in the CPU
-tests of this logic) is the plumbing."""
-from typing import Callable, List, Sequence, Tuple
+is sharded across ranks with NO collective inside the loop; the only exchange is ONE all-gather of the packed results
+(coordinates, atom classes, bond matrices: ~2.4 kB per molecule).  One process per GPU; `torch.distributed` (NCCL on
+GPUs, gloo in the CPU tests of this logic) is the plumbing.
+
+The device noise is keyed by (seed, global sample id) with a per-sample id array (`mlcg_noise.sample_ids`), so a shard
+may be ANY subset of the samples: every rank runs its whole shard as one launch sequence (sub-batched only to bound
+memory) and the sharded result equals the single-GPU result bit for bit."""
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+SEER_D = 42
 
 
 def sample_cost(n_nodes: np.ndarray) -> np.ndarray:
@@ -16,82 +22,101 @@ def sample_cost(n_nodes: np.ndarray) -> np.ndarray:
 
 
 def shard_indices(n_nodes: Sequence[int], world_size: int) -> List[np.ndarray]:
-    """Deterministic, cost-balanced partition of sample ids over ranks (longest-processing-time greedy).  Each rank's
-    list is sorted, so a rank's samples keep their global order; per-sample RNG is keyed by global id, hence any
-    partition reproduces the single-GPU result."""
+    """Deterministic, cost-balanced partition of the sample ids over the ranks: samples sorted by cost (stable) are dealt
+    in snake order (0..W-1, W-1..0, ...), so every rank gets the same number of samples (+-1) of every size class and
+    the same total cost to within one sample.  Each rank's ids are returned sorted ascending.  Every rank computes the
+    same partition from `n_nodes` alone -- no communication."""
     n_nodes = np.asarray(n_nodes)
-    cost = sample_cost(n_nodes)
-    order = np.argsort(-cost, kind="stable")
-    loads = np.zeros(world_size)
-    buckets: List[List[int]] = [[] for _ in range(world_size)]
-    for idx in order:
-        r = int(np.argmin(loads))
-        buckets[r].append(int(idx))
-        loads[r] += cost[idx]
-    return [np.sort(np.asarray(b, dtype=np.int64)) for b in buckets]
+    order = np.argsort(-sample_cost(n_nodes), kind="stable")
+    pos = np.arange(order.size)
+    lap, k = pos // world_size, pos % world_size
+    rank_of = np.where(lap % 2 == 0, k, world_size - 1 - k)
+    return [np.sort(order[rank_of == r]).astype(np.int64) for r in range(world_size)]
 
 
-def contiguous_runs(ids: np.ndarray) -> List[Tuple[int, int]]:
-    """[(start, length)] runs of consecutive global ids (the device RNG takes one sample_offset per launch)."""
-    runs, start, prev = [], None, None
-    for i in ids.tolist():
-        if start is None:
-            start = prev = i
-        elif i == prev + 1:
-            prev = i
-        else:
-            runs.append((start, prev - start + 1))
-            start = prev = i
-    if start is not None:
-        runs.append((start, prev - start + 1))
-    return runs
+def result_bytes(max_n_nodes: int) -> int:
+    return max_n_nodes * 3 * 4 + max_n_nodes * 4 + SEER_D * SEER_D
 
 
-def gather_results(local: Sequence[torch.Tensor], local_ids: np.ndarray, total: int, group=None) -> List[torch.Tensor]:
-    """The single collective of the path: all-gather every rank's (ids, tensors...) and scatter them back into global
-    sample order.  Shards may differ in size: they are padded to the largest shard for the fixed-size all_gather."""
+def pack_results(x: torch.Tensor, cls: torch.Tensor, bonds: torch.Tensor) -> torch.Tensor:
+    """(n,N,3) f32, (n,N) i32, (n,42,42) i8 -> (n, result_bytes(N)) uint8: one buffer, one collective."""
+    n = x.shape[0]
+    return torch.cat([x.contiguous().view(torch.uint8).reshape(n, -1), cls.contiguous().view(torch.uint8).reshape(n, -1),
+                      bonds.contiguous().view(torch.uint8).reshape(n, -1)], dim=1)
+
+
+def unpack_results(buf: torch.Tensor, max_n_nodes: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    n, N = buf.shape[0], max_n_nodes
+    a, b = N * 12, N * 16
+    x = buf[:, :a].clone().view(torch.float32).reshape(n, N, 3)
+    cls = buf[:, a:b].clone().view(torch.int32).reshape(n, N)
+    bonds = buf[:, b:].clone().view(torch.int8).reshape(n, SEER_D, SEER_D)
+    return x, cls, bonds
+
+
+def gather_packed(local: torch.Tensor, shards: List[np.ndarray], total: int, group=None) -> torch.Tensor:
+    """The single collective of the path.  `local` (len(shards[rank]), W) holds this rank's rows in the order of
+    shards[rank]; returns (total, W) in global sample order on every rank.  Shards may differ in size (or be empty): they
+    are padded to the largest shard for the fixed-size all-gather; the shard lists are known on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    width = local.shape[1]
+    full = torch.zeros((total, width), dtype=local.dtype, device=local.device)
     if world == 1:
-        outs = []
-        for t in local:
-            full = torch.zeros((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            full[torch.as_tensor(local_ids, device=t.device)] = t
-            outs.append(full)
-        return outs
-    dev = local[0].device
-    n_local = torch.tensor([len(local_ids)], device=dev, dtype=torch.int64)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    cap = int(max(int(s) for s in sizes))
-    ids_pad = torch.full((cap,), -1, dtype=torch.int64, device=dev)
-    ids_pad[: len(local_ids)] = torch.as_tensor(local_ids, device=dev)
-    all_ids = [torch.empty_like(ids_pad) for _ in range(world)]
-    dist.all_gather(all_ids, ids_pad, group=group)
-    outs = []
-    for t in local:
-        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        pad[: t.shape[0]] = t
-        parts = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(parts, pad, group=group)
-        full = torch.zeros((total,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        for r in range(world):
-            k = int(sizes[r])
-            full[all_ids[r][:k]] = parts[r][:k]
-        outs.append(full)
-    return outs
+        full[torch.as_tensor(shards[0], device=local.device)] = local
+        return full
+    cap = max(len(s) for s in shards)
+    if cap == 0:
+        return full
+    pad = torch.zeros((cap, width), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    allp = torch.empty((world * cap, width), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(allp, pad, group=group)
+    allp = allp.view(world, cap, width)
+    for r in range(world):
+        k = len(shards[r])
+        if k:
+            full[torch.as_tensor(shards[r], device=local.device)] = allp[r, :k]
+    assert local.shape[0] == len(shards[rank])
+    return full
 
 
-def generate_sharded(run_shard: Callable[[np.ndarray, np.ndarray, int], Sequence[torch.Tensor]], n_nodes: Sequence[int],
-                     group=None) -> List[torch.Tensor]:
-    """Shard `n_nodes` over the ranks of `group`, call `run_shard(ids, n_nodes[ids], sample_offset)` for every contiguous
-    run of this rank's ids, gather.  `run_shard` is the per-GPU hot path (e.g. Engine.generate_host)."""
+def generate_sharded(run_shard: Callable[[np.ndarray, np.ndarray], Sequence[torch.Tensor]], n_nodes: Sequence[int],
+                     max_n_nodes: int, group=None, max_batch: int = 8192, device: Optional[torch.device] = None,
+                     stats: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Shards `n_nodes` over the ranks of `group`; this rank calls `run_shard(ids, n_nodes[ids])` -- the per-GPU hot path,
+    e.g. `Engine.generate_host(..., sample_ids=ids, device_out=True)` -- once per sub-batch of at most `max_batch` of its
+    samples (one call for a shard that fits), packs the results and runs the one all-gather.  Returns
+    (x (B,N,3) f32, atom_class (B,N) i32, bonds (B,42,42) i8) for ALL samples in global order, on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n_nodes = np.asarray(n_nodes)
-    mine = shard_indices(n_nodes, world)[rank]
-    pieces: List[Sequence[torch.Tensor]] = []
-    for start, length in contiguous_runs(mine):
-        ids = np.arange(start, start + length)
-        pieces.append(run_shard(ids, n_nodes[ids], start))
-    local = [torch.cat([p[k] for p in pieces], dim=0) for k in range(len(pieces[0]))] if pieces else []
-    return gather_results(local, mine, len(n_nodes), group)
+    shards = shard_indices(n_nodes, world)
+    mine = shards[rank]
+    pieces = []
+    for s in range(0, len(mine), max_batch):
+        ids = mine[s:s + max_batch]
+        x, cls, bonds = run_shard(ids, n_nodes[ids])
+        pieces.append(pack_results(x, cls, bonds))
+    if stats is not None:
+        stats["calls"] = len(pieces)
+        stats["shard"] = len(mine)
+    if pieces:
+        local = torch.cat(pieces, dim=0) if len(pieces) > 1 else pieces[0]
+    else:
+        local = torch.zeros((0, result_bytes(max_n_nodes)), dtype=torch.uint8, device=device or torch.device("cpu"))
+    full = gather_packed(local, shards, len(n_nodes), group)
+    return unpack_results(full, max_n_nodes)
+
+
+def generate_sharded_engine(engine, n_nodes: Sequence[int], max_n_nodes: int, ctx: np.ndarray, T: int = 100,
+                            resample_steps: int = 0, seed: int = 0, group=None, max_batch: int = 8192,
+                            stats: Optional[dict] = None):
+    """`generate_sharded` driving `Engine.generate_host` (device outputs): the multi-GPU product path.  ctx: (B,3)
+    normalised context of every sample."""
+    ctx = np.asarray(ctx, dtype=np.float32).reshape(-1, 3)
+
+    def run_shard(ids, nn):
+        return engine.generate_host(nn, max_n_nodes, ctx[ids], T, resample_steps, seed=seed, sample_ids=ids, device_out=True)
+
+    return generate_sharded(run_shard, n_nodes, max_n_nodes, group, max_batch, engine.device, stats)
