@@ -193,6 +193,14 @@ int64_t mlcg_kernel_launches(mlcg_handle* h);    /* kernels launched by this han
  * times on the current batch state and returns the mean milliseconds per launch (< 0 on error). */
 float mlcg_time_edge_kernel(mlcg_handle* h, int layer, int iters, void* stream);
 
+/* Measurement: one EGNN forward (same arguments as mlcg_egnn_forward) with a CUDA event after every launch.
+ * out_ms[c] = milliseconds in kernel class c: 0 prepare (k_egnn_prepare), 1 P/Q projection GEMMs, 2 fused edge kernel
+ * (GCL sub-layers), 3 fused edge kernel (equivariant sub-layers), 4 split-target fix-ups, 5 first node-MLP GEMM,
+ * 6 second node-MLP GEMM (residual), 7 readout; out_ms[8] = the whole forward; out_ms[9 + c] = launches of class c.
+ * out_ms must hold 17 doubles.  Synchronous. */
+int mlcg_egnn_forward_breakdown(mlcg_handle* h, const float* t, const float* z, const float* ctx, float* eps,
+                                double* out_ms, void* stream);
+
 /* Diagnostics: mean cycles per 128-row tile spent in each phase of the fused edge kernel for `layer` on the current
  * batch: out[0] row-info + P/Q wait, [1] A generation, [2] MMA tail, [3] epilogue pass 1, [4] pass 2 / coordinate
  * update, [5] A-ring back-pressure (part of [1]), [6] tiles profiled, [7..10] pass-2 sub-phases (wait for the

@@ -18,6 +18,7 @@ EXPORTS = [
     "mlcg_decode", "mlcg_sample", "mlcg_seer_inputs", "mlcg_seer_forward", "mlcg_generate", "mlcg_num_edge_tiles",
     "mlcg_num_edges", "mlcg_kernel_launches", "mlcg_time_edge_kernel", "mlcg_edge_phase_profile", "mlcg_test_gemm",
     "mlcg_shape_moments", "mlcg_shape_tanimoto", "mlcg_gemm_phase_profile", "mlcg_plan_edge_tiles",
+    "mlcg_egnn_forward_breakdown",
 ]
 
 
@@ -35,12 +36,29 @@ class StepScalars(C.Structure):
                 ("alpha_s", C.c_float), ("sigma_s", C.c_float), ("blend", C.c_float)]
 
 
+STAMP_PATH = LIB_PATH + ".stamp"
+BUILD_INFO = {"action": None, "sources_sha256": None}
+
+
+def sources_digest() -> str:
+    """sha256 over the CUDA sources + the C header: identifies the source state a binary was compiled from."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in SOURCES + [HEADER]:
+        h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libmlcg_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(p) for p in SOURCES + [HEADER])
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+    """Compile libmlcg_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).  The binary carries a stamp with
+    the digest of the sources it was compiled from; it is rebuilt whenever the stamp does not match the sources in the
+    tree (file times do not survive a snapshot), so a stale or foreign binary is never used.  BUILD_INFO records whether
+    this call compiled or found a binary of exactly these sources."""
+    digest = sources_digest()
+    BUILD_INFO["sources_sha256"] = digest
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH) and open(STAMP_PATH).read().strip() == digest:
+        BUILD_INFO["action"] = "up to date (binary stamp == sha256 of the sources in the tree)"
+        return LIB_PATH
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC", "-I" + os.path.join(_ROOT, "include"), "-o", LIB_PATH, SOURCES[0]]
     if verbose:
@@ -48,6 +66,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    with open(STAMP_PATH, "w") as fh:
+        fh.write(digest + "\n")
+    BUILD_INFO["action"] = "compiled with nvcc"
     return LIB_PATH
 
 
@@ -74,6 +95,7 @@ def load() -> C.CDLL:
     lib.mlcg_load_seer.argtypes = [vp, C.POINTER(WeightDesc), ci]
     lib.mlcg_set_batch.argtypes = [vp, vp, ci, ci]
     lib.mlcg_egnn_forward.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.mlcg_egnn_forward_breakdown.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_double), vp]
     lib.mlcg_noise_init.argtypes = [vp, vp, C.POINTER(Noise), vp]
     lib.mlcg_step.argtypes = [vp, vp, vp, C.POINTER(StepScalars), C.POINTER(Noise), vp]
     lib.mlcg_reinject.argtypes = [vp, vp, vp, vp, C.POINTER(StepScalars), C.POINTER(Noise), vp]

@@ -97,6 +97,9 @@ struct mlcg_handle {
   int gen_key_hits = 0;            // calls seen with the current key (1st runs eagerly, 2nd captures)
   long long gen_graph_launches = 0;
   cudaStream_t own_stream = nullptr;  // used by mlcg_generate when the caller passes the NULL stream (not capturable)
+  // mlcg_egnn_forward_breakdown: events recorded after every launch of one forward, tagged with a kernel class
+  bool bd_on = false;
+  std::vector<std::pair<int, cudaEvent_t>> bd_ev;
   int kc448() const { return HP / epc(precision == PREC_BF16 ? PREC_BF16 : PREC_TF32); }
 };
 
@@ -120,6 +123,17 @@ struct mlcg_handle {
   } while (0)
 
 static thread_local std::string g_create_err;
+
+// kernel classes of one EGNN forward (mlcg_egnn_forward_breakdown)
+enum { BD_START = -1, BD_PREPARE = 0, BD_PQ = 1, BD_EDGE_GCL = 2, BD_EDGE_EQUIV = 3, BD_FIXUP = 4, BD_MLP1 = 5, BD_MLP2 = 6,
+       BD_READOUT = 7, BD_NCLASS = 8 };
+static void bd_mark(mlcg_handle* h, int cls, cudaStream_t st) {
+  if (!h->bd_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  h->bd_ev.emplace_back(cls, e);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel launch helpers
@@ -743,6 +757,7 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
   float* xb = h->xb.as<float>();
   CK(gemm_pq(h->layers[0]));
   h->launches++;
+  bd_mark(h, BD_PQ, st);
   for (int l = 0; l < 27; ++l) {
     const LayerW& L = h->layers[l];
     const int blk = l / 3;
@@ -751,7 +766,9 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
     EdgeArgs ea = edge_args(h, L, x_cur, x_next);
     CK(launch_edge_mode(mode, L.equiv, ea, grid_e, st));
     h->launches++;
+    bd_mark(h, L.equiv ? BD_EDGE_EQUIV : BD_EDGE_GCL, st);
     CK(launch_edge_fixup(h, mode, L.equiv, ea, st));
+    bd_mark(h, BD_FIXUP, st);
     if (!L.equiv) {
       GemmArgs a{};
       a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc;
@@ -760,16 +777,19 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
       a.out_op = h->t_op.as<uint8_t>(); a.out_op_chunks = kc;
       CK((launch_gemm_mode<HP, EPI_SILU_OP>(mode, a, h->n_mtiles, 1, st)));
       h->launches++;
+      bd_mark(h, BD_MLP1, st);
       GemmArgs b{};
       b.a0 = h->t_op.as<uint8_t>(); b.a0_chunks = kc; b.a0_per_tile = kc; b.n_kc = kc;
       b.w = L.w4_op.as<uint8_t>(); b.bias = L.b4p.as<float>(); b.m_rows = h->M;
       b.out_op = h->h_op.as<uint8_t>(); b.out_op_chunks = kc; b.resid = h->h_res.as<float>(); b.ldr = 0;  // tiled residual layout
       CK((launch_gemm_mode<HP, EPI_RESID_OP>(mode, b, h->n_mtiles, 1, st)));
       h->launches++;
+      bd_mark(h, BD_MLP2, st);
     }
     if (l + 1 < 27) {
       CK(gemm_pq(h->layers[l + 1]));
       h->launches++;
+      bd_mark(h, BD_PQ, st);
     }
   }
   return MLCG_OK;
@@ -836,6 +856,7 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
   if (!t || !z || !ctx || !eps) FAIL(MLCG_E_ARG, "egnn_forward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = h->kc448();
+  bd_mark(h, BD_START, st);
   if (h->precision == PREC_BF16)
     k_egnn_prepare<PREC_BF16><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M, h->w_emb.d,
                                                   h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
@@ -849,12 +870,41 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
                                                        h->w_emb.d, h->b_emb.d, h->h_res.as<float>(), HP, nullptr, 0,
                                                        h->x0.as<float>(), h->xa.as<float>());
   KCHECK();
+  bd_mark(h, BD_PREPARE, st);
   int rc = (h->precision == PREC_FP32_SIMT) ? egnn_forward_simt(h, st) : egnn_forward_tc(h, st);
   if (rc) return rc;
   // 9 blocks: blocks 0,2,4,6,8 write xb -> final coordinates are in xb
   k_egnn_readout<<<h->B, 256, 0, st>>>(h->h_res.as<float>(), h->precision == PREC_FP32_SIMT ? HP : 0, h->xb.as<float>(), h->x0.as<float>(), h->d_n_nodes.as<int>(),
                                        h->d_node_off.as<int>(), h->N, h->w_out.d, h->b_out.d, eps);
   KCHECK();
+  bd_mark(h, BD_READOUT, st);
+  return MLCG_OK;
+}
+
+/* One EGNN forward with a CUDA event after every launch: out_ms[c] = milliseconds spent in kernel class c
+ * (0 prepare, 1 P/Q projections, 2 edge kernel GCL, 3 edge kernel equivariant, 4 split-target fix-ups, 5 node MLP 1,
+ * 6 node MLP 2, 7 readout), out_ms[8] = whole forward, out_ms[9..16] = launches per class.  Synchronous. */
+extern "C" int mlcg_egnn_forward_breakdown(mlcg_handle* h, const float* t, const float* z, const float* ctx, float* eps,
+                                           double* out_ms, void* stream) {
+  if (!h || !out_ms) return MLCG_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  h->bd_on = true;
+  h->bd_ev.clear();
+  int rc = mlcg_egnn_forward(h, t, z, ctx, eps, stream);
+  h->bd_on = false;
+  cudaError_t ce = cudaStreamSynchronize(st);
+  for (int k = 0; k < 2 * BD_NCLASS + 1; ++k) out_ms[k] = 0.0;
+  for (size_t i = 1; i < h->bd_ev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->bd_ev[i - 1].second, h->bd_ev[i].second);
+    const int c = h->bd_ev[i].first;
+    if (c >= 0 && c < BD_NCLASS) { out_ms[c] += ms; out_ms[BD_NCLASS + 1 + c] += 1.0; }
+    out_ms[BD_NCLASS] += ms;
+  }
+  for (auto& e : h->bd_ev) cudaEventDestroy(e.second);
+  h->bd_ev.clear();
+  if (rc) return rc;
+  CK(ce);
   return MLCG_OK;
 }
 

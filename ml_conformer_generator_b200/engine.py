@@ -106,6 +106,22 @@ class Engine:
                     "egnn_forward")
         return eps
 
+    BREAKDOWN_CLASSES = ["prepare", "pq_projection", "edge_gcl", "edge_equiv", "edge_fixup", "node_mlp1", "node_mlp2",
+                         "readout"]
+
+    def egnn_forward_breakdown(self, t: torch.Tensor, z: torch.Tensor, ctx: torch.Tensor) -> dict:
+        """One EGNN forward with a CUDA event after every launch: {class: (ms, launches)} + 'total' (measurement hook)."""
+        t = t.reshape(-1).to(self.device, torch.float32).contiguous()
+        z = z.to(self.device, torch.float32).contiguous()
+        ctx = ctx.to(self.device, torch.float32).contiguous()
+        eps = torch.empty_like(z)
+        out = (C.c_double * 17)()
+        self._check(self.lib.mlcg_egnn_forward_breakdown(self.h, _ptr(t), _ptr(z), _ptr(ctx), _ptr(eps), out, self._stream()),
+                    "egnn_forward_breakdown")
+        res = {n: {"ms": float(out[i]), "launches": int(out[9 + i])} for i, n in enumerate(self.BREAKDOWN_CLASSES)}
+        res["total_ms"] = float(out[8])
+        return res
+
     def _steps(self, T: int, blend_power: int):
         gamma = gamma_table(T)
         sc = all_step_scalars(gamma)

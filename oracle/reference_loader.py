@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *real* reference (`/root/reference/src/mlconfgen`) in this
 container so the oracle port (`oracle/edm_oracle.py`) can be validated against it and golden vectors
-generated (`oracle/make_golden.py`).  `/root/reference` does not exist on the GPU box: nothing in
-`tests -m gpu`, `smoke()` or `bench.py` may import this module.
+generated (`oracle/make_golden.py`).  `/root/reference` does not exist on the GPU box; there the
+loader falls back to the staged unmodified copy `oracle/_ref` (recipe: oracle/build_ref.py, git-ignored).  Only tests,
+`smoke()` and the reference / cpu_baseline legs of `bench.py` may import this module -- never the product.
 
 rdkit is not installed here; the hot-path modules (egnn.py, equivariant_diffusion.py, adj_mat_seer.py,
 the tensor half of utils/mol_utils.py) are pure torch, so rdkit is stubbed in sys.modules.
@@ -19,16 +20,31 @@ _STUBS = [
 ]
 
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_path(path: str = None) -> str:
+    """/root/reference/src in the build container; the staged unmodified copy oracle/_ref (oracle/build_ref.py) on the
+    GPU box, where /root/reference does not exist."""
+    if path:
+        return path
+    if os.environ.get("MLCG_REF"):
+        return os.environ["MLCG_REF"]
+    for cand in ("/root/reference/src", _STAGED):
+        if os.path.isdir(os.path.join(cand, "mlconfgen")):
+            return cand
+    return "/root/reference/src"
+
+
 def reference_available(path: str = None) -> bool:
-    path = path or os.environ.get("MLCG_REF", "/root/reference/src")
-    return os.path.isdir(os.path.join(path, "mlconfgen"))
+    return os.path.isdir(os.path.join(reference_path(path), "mlconfgen"))
 
 
 def load_reference(path: str = None):
     """Returns the imported `mlconfgen` package of the reference."""
-    path = path or os.environ.get("MLCG_REF", "/root/reference/src")
+    path = reference_path(path)
     if not reference_available(path):
-        raise RuntimeError("reference not present at %s" % path)
+        raise RuntimeError("reference not present at %s (run `python -m oracle.build_ref` in the build container)" % path)
     for name in _STUBS:
         if name not in sys.modules:
             sys.modules[name] = MagicMock()

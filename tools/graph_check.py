@@ -10,7 +10,7 @@ for name, T in (("C1", 100), ("C2", 10)):
     outs = []
     for k in range(4):
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        o = e.generate_host(wl["n_nodes"], wl["N"], ctx, T, 0, seed=5 + (k == 3))
+        o = e.generate_host(wl["global_n_nodes"], wl["N"], ctx, T, 0, seed=5 + (k == 3))
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         outs.append([t.clone() for t in o]); print(name, "call", k, "%.1f ms" % (dt * 1e3), "launches", e.kernel_launches())
     same = all(torch.equal(a, b) for a, b in zip(outs[0], outs[1])) and all(torch.equal(a, b) for a, b in zip(outs[0], outs[2]))

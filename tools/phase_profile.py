@@ -10,7 +10,7 @@ wl = workload(sys.argv[2] if len(sys.argv) > 2 else "C2")
 e = Engine(torch.device("cuda:0"), prec)
 sd, ssd = random_state_dicts(0)
 e.load_edm_state_dict(sd)
-e.set_batch(wl["n_nodes"], wl["N"])
+e.set_batch(wl["global_n_nodes"], wl["N"])
 B, N = wl["B"], wl["N"]
 z = torch.randn(B, N, 11, device="cuda")
 e.egnn_forward(torch.full((B,), 0.5), z, torch.from_numpy(normed_ctx(wl["ctx"], B)))
