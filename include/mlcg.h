@@ -32,7 +32,10 @@ typedef struct mlcg_handle mlcg_handle;
 enum {
   MLCG_PREC_FP32 = 0, /* exact fp32 SIMT kernels (on-GPU reference mode; edge tensors staged through HBM) */
   MLCG_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate -- parity mode (eps within 1e-3 relative) */
-  MLCG_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream -- fast mode */
+  MLCG_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, fp32 residual stream */
+  MLCG_PREC_FP16 = 3  /* tcgen05 kind::f16 (fp16 operands: tf32's 10-bit mantissa at bf16's rate), fp32 accumulate, fp32
+                         residual stream; every 16-bit quantity carries an exact power-of-two range scale whose inverse is
+                         folded into the packed weights -- the fast mode that also meets the tf32 parity numbers */
 };
 
 enum {
@@ -152,6 +155,27 @@ int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B, int N, con
                   uint64_t seed, int64_t sample_offset, const int64_t* sample_ids_host, float* x_out,
                   int32_t* atom_class_out, int8_t* bonds_out, void* stream);
 
+/* ---- Inertial fragment matching (the default fragment mode) between the two reverse loops ---------------------------
+ * Replaces: ifm_prepare_gen_fragment_context (utils/mol_utils.py:373-457) after its batch-independent prologue.  The
+ * caller computes once, on the host and in float32 as the reference does, moi_gen_origin_host (3x3 row-major) =
+ * diag(reference_context) - MOI(fixed fragment) (:396-409) and ff_weighted_com_host (3) = n_ff * mean(fixed fragment
+ * coordinates) (:411); norm_mean_host / norm_mad_host (3 each) are CONTEXT_NORMS.  Per sample b (n_nodes[b] = total atoms,
+ * DEVICE int32): n_gen = n_nodes - n_ff, shift = ff_weighted_com / n_gen, the inverse parallel-axis shift
+ * (shift_moi_to_com_batch, :527-550), the symmetric 3x3 eigen-decomposition (torch.linalg.eigh in the reference; cyclic
+ * Jacobi here, eigenvalues ascending, each eigenvector signed so that its largest component is positive -- an eigenvector's
+ * sign is the solver's choice) and the normalised context.  Outputs (DEVICE): ctx (B,3), shift (B,3), rot (B,3,3, columns
+ * = eigenvectors), n_gen (B) int32. */
+int mlcg_ifm_context(mlcg_handle* h, const float* moi_gen_origin_host, const float* ff_weighted_com_host, int n_ff,
+                     const float* norm_mean_host, const float* norm_mad_host, const int32_t* n_nodes, int B, float* ctx_out,
+                     float* shift_out, float* rot_out, int32_t* n_gen_out, void* stream);
+/* Replaces: inverse_coord_transform (utils/mol_utils.py:508-524) + ifm_prepare_fragments_for_merge (:460-505) on the
+ * device outputs of the first loop.  x_gen (B,Ng,3), cls_gen (B,Ng) int32 (-1 = padding), shift (B,3), rot (B,3,3),
+ * ff_x (n_ff,3), ff_h (n_ff,8) raw 0/1 one-hot -> z_known (B,N,11), fixed_mask (B,N) float; N >= n_ff, atoms beyond
+ * n_ff + Ng are zero.  All DEVICE pointers. */
+int mlcg_ifm_merge_inputs(mlcg_handle* h, const float* x_gen, const int32_t* cls_gen, const float* shift, const float* rot,
+                          const float* ff_x, const float* ff_h, int n_ff, int B, int Ng, int N, float* z_known,
+                          float* fixed_mask, void* stream);
+
 /* ---- Gaussian shape similarity (the tensor part of the reference's evaluate_samples) -------------------------------
  * Replaces get_shape_quadrupole_for_molecule (cheminformatics/shape_similarity.py:18-203: clique enumeration :267-311 and
  * the inclusion-exclusion moment series) up to the 3x3 eigen-decomposition, which stays on the host (torch.linalg.eigh,
@@ -216,7 +240,7 @@ int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, void* stream
 int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, void* stream);
 
 /* Test hook: C[M x N] = A[M x K] . W[N x K]^T + bias through the tcgen05 GEMM kernel (row-major fp32 in / out,
- * converted to operand format internally).  mode = MLCG_PREC_TF32 or MLCG_PREC_BF16; bn = 448 or 256. */
+ * converted to operand format internally).  mode = MLCG_PREC_TF32, MLCG_PREC_BF16 or MLCG_PREC_FP16; bn = 448 or 256. */
 int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,
                    int M, int N, int K, void* stream);
 

@@ -144,13 +144,21 @@ class MLConformerGenerator:
         if fixed_fragment is None:
             x, h = gm(node_mask, edge_mask, ctx, resample_steps)
         elif inertial_fragment_matching:
+            # Inertial fragment matching (conformer_generator.py:178-236).  Everything between the two reverse loops --
+            # the per-sample context of the fragment to generate (inverse parallel-axis shift + 3x3 eigh), the inverse
+            # coordinate transform and the assembly of z_known / fixed_mask -- runs on the device (mlcg_ifm_*): the first
+            # loop's outputs never leave HBM.
             ff_x, ff_h = fixed_fragment
-            n_nodes = node_mask.sum(dim=1).to(torch.long)
-            f_nm, f_em, f_ctx, shift, rotation = ifm_prepare_gen_fragment_context(
-                ff_x, reference_context, self.context_norms, n_nodes, max_n_nodes, min_n_nodes)
-            x_gen, h_gen = gm(f_nm, f_em, f_ctx, resample_steps)
-            x_gen = inverse_coord_transform(x_gen.cpu(), shift.cpu(), rotation.cpu())
-            z_known, fixed_mask = ifm_prepare_fragments_for_merge(ff_x.cpu(), ff_h.cpu(), x_gen, h_gen.cpu(), max_n_nodes)
+            n_ff = int(ff_x.size(0))
+            from .mol_utils import _check_fragment_size
+            _check_fragment_size(n_ff, min_n_nodes, max_n_nodes)
+            eng = self.engine
+            n_nodes = node_mask.sum(dim=(1, 2)).to(torch.int32)
+            f_ctx, shift, rotation, n_gen = eng.ifm_context(ff_x, reference_context, self.context_norms, n_nodes)
+            n_max_frag = max_n_nodes - n_ff
+            eng.set_batch((n_nodes - n_ff).numpy(), n_max_frag)
+            x_gen, cls_gen = eng.sample(f_ctx, gm.T, "forward", resample_steps, noise_tape=gm.noise_tape, seed=gm.seed)
+            z_known, fixed_mask = eng.ifm_merge_inputs(x_gen, cls_gen, shift, rotation, ff_x, ff_h, max_n_nodes)
             x, h = gm.merge_fragments(node_mask, edge_mask, fixed_mask, ctx, z_known, ifm_diffusion_level,
                                       resample_steps, blend_power)
         else:

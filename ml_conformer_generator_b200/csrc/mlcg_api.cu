@@ -11,6 +11,7 @@
 #include "mlcg_kernels.cuh"
 #include "mlcg_tc.cuh"
 #include "mlcg_shape.cuh"
+#include "mlcg_ifm.cuh"
 
 using namespace mlcg;
 
@@ -100,7 +101,7 @@ struct mlcg_handle {
   // mlcg_egnn_forward_breakdown: events recorded after every launch of one forward, tagged with a kernel class
   bool bd_on = false;
   std::vector<std::pair<int, cudaEvent_t>> bd_ev;
-  int kc448() const { return HP / epc(precision == PREC_BF16 ? PREC_BF16 : PREC_TF32); }
+  int kc448() const { return HP / epc(is16(precision) ? PREC_BF16 : PREC_TF32); }
 };
 
 #define CK(call)                                                                              \
@@ -162,6 +163,7 @@ static cudaError_t launch_gemm(const GemmArgs& a, int n_mtiles, int n_ntiles, cu
 }
 template <int BN, int kEpi>
 static cudaError_t launch_gemm_mode(int mode, const GemmArgs& a, int n_mtiles, int n_ntiles, cudaStream_t st) {
+  if (mode == PREC_FP16) return launch_gemm<PREC_FP16, BN, kEpi>(a, n_mtiles, n_ntiles, st);
   return mode == PREC_BF16 ? launch_gemm<PREC_BF16, BN, kEpi>(a, n_mtiles, n_ntiles, st)
                            : launch_gemm<PREC_TF32, BN, kEpi>(a, n_mtiles, n_ntiles, st);
 }
@@ -247,6 +249,15 @@ static void edge_tile_owner(int num_sms, int n_tiles, std::vector<int>& owner) {
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
+  if (mode == PREC_FP16 && edge_dist_fp32()) {
+    if (pair)
+      return equiv ? launch_edge<PREC_FP16, true, true, true>(a, grid, st) : launch_edge<PREC_FP16, false, true, true>(a, grid, st);
+    return equiv ? launch_edge<PREC_FP16, true, false, true>(a, grid, st) : launch_edge<PREC_FP16, false, false, true>(a, grid, st);
+  }
+  if (mode == PREC_FP16) {
+    if (pair) return equiv ? launch_edge<PREC_FP16, true, true>(a, grid, st) : launch_edge<PREC_FP16, false, true>(a, grid, st);
+    return equiv ? launch_edge<PREC_FP16, true, false>(a, grid, st) : launch_edge<PREC_FP16, false, false>(a, grid, st);
+  }
   if (mode == PREC_BF16 && edge_dist_fp32()) {
     if (pair)
       return equiv ? launch_edge<PREC_BF16, true, true, true>(a, grid, st) : launch_edge<PREC_BF16, false, true, true>(a, grid, st);
@@ -265,12 +276,15 @@ static cudaError_t launch_edge_fixup(mlcg_handle* h, int mode, bool equiv, const
   const int* fn = h->d_fix_node.as<int>();
   if (equiv) {
     const int grid = (h->n_fix * 4 + 127) / 128;
-    if (mode == PREC_BF16)
+    if (is16(mode))  // the coordinate fix-up does not depend on the operand format
       k_edge_fixup<PREC_BF16, true><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
     else
       k_edge_fixup<PREC_TF32, true><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
   } else {
-    if (mode == PREC_BF16) {
+    if (mode == PREC_FP16) {
+      const int grid = (h->n_fix * (HP / epp(PREC_FP16)) + 127) / 128;
+      k_edge_fixup<PREC_FP16, false><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
+    } else if (mode == PREC_BF16) {
       const int grid = (h->n_fix * (HP / epp(PREC_BF16)) + 127) / 128;
       k_edge_fixup<PREC_BF16, false><<<grid, 128, 0, st>>>(fn, h->n_fix, a.fix_agg, a.fix_dx, a.agg_op, a.agg_chunks, a.x_cur, a.x_next);
     } else {
@@ -284,7 +298,8 @@ static cudaError_t launch_edge_fixup(mlcg_handle* h, int mode, bool equiv, const
 
 static cudaError_t launch_pack(int mode, const PackArgs& a, int n_ntiles, cudaStream_t st) {
   dim3 grid(a.n_kc, n_ntiles);
-  if (mode == PREC_BF16) k_pack_weight<PREC_BF16><<<grid, 256, 0, st>>>(a);
+  if (mode == PREC_FP16) k_pack_weight<PREC_FP16><<<grid, 256, 0, st>>>(a);
+  else if (mode == PREC_BF16) k_pack_weight<PREC_BF16><<<grid, 256, 0, st>>>(a);
   else k_pack_weight<PREC_TF32><<<grid, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
@@ -310,7 +325,7 @@ static NoiseSrc to_src(const mlcg_handle* h, const mlcg_noise* n) {
 extern "C" const char* mlcg_version(void) { return "mlcg_b200 0.1 (sm_100a)"; }
 
 extern "C" int mlcg_create(mlcg_handle** out, int device, int precision) {
-  if (out == nullptr || precision < 0 || precision > 2) return MLCG_E_ARG;
+  if (out == nullptr || precision < 0 || precision > 3) return MLCG_E_ARG;
   *out = nullptr;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device >= count) return MLCG_E_NO_DEVICE;
@@ -409,7 +424,10 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
   const int kc = h->kc448();
   // bf16 fast mode evaluates SiLU as h + h*tanh(h) with h = x/2: the exact factor 1/2 is folded into the packed first
   // and second edge-layer weights, their biases and the distance columns (tensor-core path only).
-  const float es = (mode == PREC_BF16) ? 0.5f : 1.0f;
+  const float es = is16(mode) ? 0.5f : 1.0f;
+  // fp16 mode: power-of-two range scales (mlcg_common.cuh): ACT on the edge pre-activations, OP on the node-level GEMM
+  // operands; the inverses are folded into the packed weights here.  Both are 1 in the other modes.
+  const float s_act = act_scale(mode), s_op = op_scale(mode);
   for (int l = 0; l < 27; ++l) {
     LayerW& L = h->layers[l];
     const int blk = l / 3, sub = l % 3;
@@ -434,8 +452,8 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       CK(cudaMemcpy(&L.att_bias, ab.d, sizeof(float), cudaMemcpyDeviceToHost));
     }
     // padded vectors (all modes)
-    if ((rc = pad_vec(h, L.wc, L.w1.d + 2 * HID, 2 * HID + 2, HID, HP, 0, -1, es))) return rc;
-    if ((rc = pad_vec(h, L.wd, L.w1.d + 2 * HID + 1, 2 * HID + 2, HID, HP, 0, -1, es))) return rc;
+    if ((rc = pad_vec(h, L.wc, L.w1.d + 2 * HID, 2 * HID + 2, HID, HP, 0, -1, es * s_act))) return rc;
+    if ((rc = pad_vec(h, L.wd, L.w1.d + 2 * HID + 1, 2 * HID + 2, HID, HP, 0, -1, es * s_act))) return rc;
     if ((rc = pad_vec(h, L.wvp, L.wv.d, 1, HID, HP))) return rc;
     if ((rc = pad_vec(h, L.bias_pq, L.b1.d, 1, HID, HP, HP, 2 * HP, es))) return rc;  // [0 | b1]
     CK(cudaMemcpy(L.h_wc, L.wc.p, HP * sizeof(float), cudaMemcpyDeviceToHost));
@@ -453,7 +471,7 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       PackArgs a{};
       a.src = L.w1.d; a.ld = 2 * HID + 2; a.n_real = HID; a.n_src_off = 0; a.bn = HP; a.n_kc = kc;
       a.seg_len = HP; a.kreal0 = HID; a.kofs0 = half * HID; a.kreal1 = 0; a.kofs1 = 0;
-      a.bias = nullptr; a.bias_k = -1; a.scale = es;
+      a.bias = nullptr; a.bias_k = -1; a.scale = es / s_op;  // the operand h arrives scaled by OP
       a.dst = L.w1ab_op.as<uint8_t>() + (size_t)half * kc * blk448;
       CK(launch_pack(mode, a, 1, 0));
       h->launches++;
@@ -471,6 +489,7 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       PackArgs a{};
       a.src = L.w3.d; a.ld = 2 * HID; a.n_real = HID; a.bn = HP; a.n_kc = 2 * kc; a.seg_len = HP;
       a.kreal0 = HID; a.kofs0 = 0; a.kreal1 = HID; a.kofs1 = HID; a.bias = nullptr; a.bias_k = -1;
+      a.scale = 1.0f / s_op;  // both operand halves (h, agg) arrive scaled by OP
       a.dst = L.w3_op.as<uint8_t>();
       CK(launch_pack(mode, a, 1, 0));
       h->launches++;
@@ -478,6 +497,7 @@ extern "C" int mlcg_load_egnn(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
       PackArgs b{};
       b.src = L.w4.d; b.ld = HID; b.n_real = HID; b.bn = HP; b.n_kc = kc; b.seg_len = HP; b.kreal0 = HID;
       b.bias = nullptr; b.bias_k = -1; b.dst = L.w4_op.as<uint8_t>();
+      b.scale = 1.0f / s_op;  // the hidden operand t arrives scaled by OP
       CK(launch_pack(mode, b, 1, 0));
       h->launches++;
     }
@@ -723,8 +743,17 @@ static EdgeArgs edge_args(mlcg_handle* h, const LayerW& L, const float* x_cur, f
   memcpy(a.wc, L.h_wc, sizeof(a.wc));
   memcpy(a.wd, L.h_wd, sizeof(a.wd));
   memcpy(a.wv, L.h_wv, sizeof(a.wv));
-  if (h->precision == PREC_BF16) {
-    auto bf = [](float f) -> uint32_t {  // round-to-nearest-even bf16 bits
+  if (is16(h->precision)) {
+    const bool f16 = (h->precision == PREC_FP16);
+    const float dinv = 1.0f / dist_scale(h->precision);  // the packed squared distances carry dist_scale
+    auto bf = [f16, dinv](float f) -> uint32_t {  // round-to-nearest-even 16-bit pattern of the distance-column weight
+      f *= dinv;
+      if (f16) {
+        const __half hv = __float2half_rn(f);
+        unsigned short us;
+        memcpy(&us, &hv, 2);
+        return us;
+      }
       uint32_t u;
       memcpy(&u, &f, 4);
       return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
@@ -750,6 +779,8 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
     a.w = L.w1ab_op.as<uint8_t>(); a.bias = L.bias_pq.as<float>(); a.m_rows = h->M;
     a.out_f32 = h->pq.as<float>(); a.ldo = 2 * HP; a.n_valid = 2 * HP; a.rowscale = nullptr; a.relu = 0;
     // bf16 mode keeps the P/Q projections in bf16 (halves their HBM and shared-memory traffic; no accuracy cost)
+    a.out_scale = act_scale(mode);  // fp16: P/Q rows are stored scaled by ACT
+    if (mode == PREC_FP16) return launch_gemm<PREC_FP16, HP, EPI_BF16>(a, h->n_mtiles, 2, st);
     if (mode == PREC_BF16) return launch_gemm<PREC_BF16, HP, EPI_BF16>(a, h->n_mtiles, 2, st);
     return launch_gemm<PREC_TF32, HP, EPI_F32>(a, h->n_mtiles, 2, st);
   };
@@ -774,7 +805,7 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
       a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc;
       a.a1 = h->agg_op.as<uint8_t>(); a.a1_per_tile = kc; a.n_kc = 2 * kc;
       a.w = L.w3_op.as<uint8_t>(); a.bias = L.b3p.as<float>(); a.m_rows = h->M;
-      a.out_op = h->t_op.as<uint8_t>(); a.out_op_chunks = kc;
+      a.out_op = h->t_op.as<uint8_t>(); a.out_op_chunks = kc; a.out_scale = op_scale(mode);
       CK((launch_gemm_mode<HP, EPI_SILU_OP>(mode, a, h->n_mtiles, 1, st)));
       h->launches++;
       bd_mark(h, BD_MLP1, st);
@@ -782,6 +813,7 @@ static int egnn_forward_tc(mlcg_handle* h, cudaStream_t st) {
       b.a0 = h->t_op.as<uint8_t>(); b.a0_chunks = kc; b.a0_per_tile = kc; b.n_kc = kc;
       b.w = L.w4_op.as<uint8_t>(); b.bias = L.b4p.as<float>(); b.m_rows = h->M;
       b.out_op = h->h_op.as<uint8_t>(); b.out_op_chunks = kc; b.resid = h->h_res.as<float>(); b.ldr = 0;  // tiled residual layout
+      b.out_scale = op_scale(mode);
       CK((launch_gemm_mode<HP, EPI_RESID_OP>(mode, b, h->n_mtiles, 1, st)));
       h->launches++;
       bd_mark(h, BD_MLP2, st);
@@ -857,7 +889,11 @@ extern "C" int mlcg_egnn_forward(mlcg_handle* h, const float* t, const float* z,
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = h->kc448();
   bd_mark(h, BD_START, st);
-  if (h->precision == PREC_BF16)
+  if (h->precision == PREC_FP16)
+    k_egnn_prepare<PREC_FP16><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M, h->w_emb.d,
+                                                  h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
+                                                  h->x0.as<float>(), h->xa.as<float>());
+  else if (h->precision == PREC_BF16)
     k_egnn_prepare<PREC_BF16><<<(h->M + PREP_NPB - 1) / PREP_NPB, HP, 0, st>>>(z, t, ctx, h->d_node_mol.as<int>(), h->d_node_off.as<int>(), h->N, h->M, h->w_emb.d,
                                                   h->b_emb.d, h->h_res.as<float>(), 0, h->h_op.as<uint8_t>(), kc,
                                                   h->x0.as<float>(), h->xa.as<float>());
@@ -1376,6 +1412,39 @@ extern "C" int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_r
   return MLCG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// inertial fragment matching between the two reverse loops (reference utils/mol_utils.py:373-550)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int mlcg_ifm_context(mlcg_handle* h, const float* moi_gen_origin_host, const float* ff_weighted_com_host, int n_ff,
+                                const float* norm_mean_host, const float* norm_mad_host, const int32_t* n_nodes, int B,
+                                float* ctx_out, float* shift_out, float* rot_out, int32_t* n_gen_out, void* stream) {
+  if (!h) return MLCG_E_ARG;
+  if (!moi_gen_origin_host || !ff_weighted_com_host || !norm_mean_host || !norm_mad_host || !n_nodes || !ctx_out || !shift_out ||
+      !rot_out || !n_gen_out || B <= 0 || n_ff <= 0)
+    FAIL(MLCG_E_ARG, "ifm_context: bad argument");
+  IfmArgs a{};
+  memcpy(a.moi0, moi_gen_origin_host, sizeof(a.moi0));
+  memcpy(a.ffsum, ff_weighted_com_host, sizeof(a.ffsum));
+  memcpy(a.mean, norm_mean_host, sizeof(a.mean));
+  memcpy(a.mad, norm_mad_host, sizeof(a.mad));
+  a.n_ff = n_ff;
+  k_ifm_context<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_nodes, B, a, ctx_out, shift_out, rot_out, n_gen_out);
+  KCHECK();
+  return MLCG_OK;
+}
+
+extern "C" int mlcg_ifm_merge_inputs(mlcg_handle* h, const float* x_gen, const int32_t* cls_gen, const float* shift,
+                                     const float* rot, const float* ff_x, const float* ff_h, int n_ff, int B, int Ng, int N,
+                                     float* z_known, float* fixed_mask, void* stream) {
+  if (!h) return MLCG_E_ARG;
+  if (!x_gen || !cls_gen || !shift || !rot || !ff_x || !ff_h || !z_known || !fixed_mask || B <= 0 || n_ff <= 0 || Ng <= 0 ||
+      N < n_ff || N > 64)
+    FAIL(MLCG_E_ARG, "ifm_merge_inputs: bad argument");
+  k_ifm_merge_inputs<<<B, 64, 0, (cudaStream_t)stream>>>(x_gen, cls_gen, shift, rot, ff_x, ff_h, n_ff, Ng, N, z_known, fixed_mask);
+  KCHECK();
+  return MLCG_OK;
+}
+
 extern "C" int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, void* stream) {
   if (!h || !out) return MLCG_E_ARG;
   if (!h->egnn_loaded || !h->batch_set || h->precision == PREC_FP32_SIMT || which < 0 || which > 2)
@@ -1390,6 +1459,7 @@ extern "C" int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, v
   GemmArgs a{};
   a.prof = buf.as<long long>();
   a.m_rows = h->M;
+  a.out_scale = (which == 0) ? act_scale(mode) : op_scale(mode);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
@@ -1398,7 +1468,8 @@ extern "C" int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, v
     a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
     a.w = L.w1ab_op.as<uint8_t>(); a.bias = L.bias_pq.as<float>();
     a.out_f32 = h->pq.as<float>(); a.ldo = 2 * HP; a.n_valid = 2 * HP;
-    if (mode == PREC_BF16) CK((launch_gemm<PREC_BF16, HP, EPI_BF16>(a, h->n_mtiles, 2, st)));
+    if (mode == PREC_FP16) CK((launch_gemm<PREC_FP16, HP, EPI_BF16>(a, h->n_mtiles, 2, st)));
+    else if (mode == PREC_BF16) CK((launch_gemm<PREC_BF16, HP, EPI_BF16>(a, h->n_mtiles, 2, st)));
     else CK((launch_gemm<PREC_TF32, HP, EPI_F32>(a, h->n_mtiles, 2, st)));
   } else if (which == 1) {
     a.a0 = h->h_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc;
@@ -1432,7 +1503,7 @@ extern "C" int mlcg_gemm_phase_profile(mlcg_handle* h, int which, double* out, v
 extern "C" int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, const float* w, const float* bias, float* c,
                               int M, int N, int K, void* stream) {
   if (!h) return MLCG_E_ARG;
-  if ((mode != PREC_TF32 && mode != PREC_BF16) || (bn != 448 && bn != 256) || !a || !w || !bias || !c || M <= 0 || N <= 0 || K <= 0)
+  if ((mode != PREC_TF32 && mode != PREC_BF16 && mode != PREC_FP16) || (bn != 448 && bn != 256) || !a || !w || !bias || !c || M <= 0 || N <= 0 || K <= 0)
     FAIL(MLCG_E_ARG, "test_gemm: bad argument");
   if (N % 4 != 0) FAIL(MLCG_E_ARG, "test_gemm: N must be a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1444,7 +1515,8 @@ extern "C" int mlcg_test_gemm(mlcg_handle* h, int mode, int bn, const float* a, 
   CK(cudaMemsetAsync(h->tg_b.p, 0, (size_t)nt * bn * 4, st));
   CK(cudaMemcpyAsync(h->tg_b.p, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
   const long long pieces = (long long)M * kc * 8;
-  if (mode == PREC_BF16) k_rowmajor_to_op<PREC_BF16><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a, K, M, K, h->tg_a.as<uint8_t>(), kc);
+  if (mode == PREC_FP16) k_rowmajor_to_op<PREC_FP16><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a, K, M, K, h->tg_a.as<uint8_t>(), kc);
+  else if (mode == PREC_BF16) k_rowmajor_to_op<PREC_BF16><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a, K, M, K, h->tg_a.as<uint8_t>(), kc);
   else k_rowmajor_to_op<PREC_TF32><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a, K, M, K, h->tg_a.as<uint8_t>(), kc);
   KCHECK();
   PackArgs pa{};

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -25,12 +26,31 @@ constexpr int SEER_H = 2048;
 constexpr int SEER_E = 64;
 constexpr int SEER_NB = 5;
 
-enum Precision { PREC_FP32_SIMT = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
+enum Precision { PREC_FP32_SIMT = 0, PREC_TF32 = 1, PREC_BF16 = 2, PREC_FP16 = 3 };
+// the two 16-bit tensor-core modes (tcgen05 kind::f16) share every kernel; they differ in the operand format only
+__host__ __device__ constexpr bool is16(int mode) { return mode == PREC_BF16 || mode == PREC_FP16; }
 
 // elements per 128-byte operand chunk row
-__host__ __device__ constexpr int epc(int mode) { return mode == PREC_BF16 ? 64 : 32; }
+__host__ __device__ constexpr int epc(int mode) { return is16(mode) ? 64 : 32; }
 // elements per 16-byte piece
-__host__ __device__ constexpr int epp(int mode) { return mode == PREC_BF16 ? 8 : 4; }
+__host__ __device__ constexpr int epp(int mode) { return is16(mode) ? 8 : 4; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp16 mode: range management.  fp16 has tf32's 10-bit mantissa (8x finer than bf16) at bf16's tensor-core rate, but
+// only 5 exponent bits (max 65504).  Every 16-bit quantity of the hot path is therefore stored with an exact
+// power-of-two scale whose inverse is folded into the consumer (weights packed at load time, fp32 epilogue constants):
+//   edge pre-activations / activations / messages   x ACT  (2^-6):  |value| up to 4e6 representable
+//   squared distances (packed evaluation)           x DIST (2^-10): d^2 up to 6.7e7
+//   node-level GEMM operands h, agg, t              x OP   (2^-4)
+// bf16 mode uses scale 1 everywhere (fp32 exponent range).  Scales are powers of two: no rounding is introduced.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr float act_scale(int mode) { return mode == PREC_FP16 ? 0.015625f : 1.0f; }
+__host__ __device__ constexpr float dist_scale(int mode) { return mode == PREC_FP16 ? 0.0009765625f : 1.0f; }
+__host__ __device__ constexpr float op_scale(int mode) { return mode == PREC_FP16 ? 0.0625f : 1.0f; }
+// neighbour aggregate: the segment sum holds ACT * sum(e); stored value = OP * sum(e) / 100
+__host__ __device__ constexpr float agg_out_scale(int mode) { return 0.01f / act_scale(mode) * op_scale(mode); }
+// tcgen05 instruction-descriptor operand format: kind::f16 -> 0 = F16, 1 = BF16; kind::tf32 -> 2
+__host__ __device__ constexpr int umma_fmt(int mode) { return mode == PREC_FP16 ? 0 : (mode == PREC_BF16 ? 1 : 2); }
 
 // byte offset of (row r, 16-byte piece p) inside a SWIZZLE_128B K-major chunk whose base is 1024-byte aligned:
 // Swizzle<3,4,3>: address bits [4,7) ^= bits [7,10).
@@ -85,6 +105,72 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// packed 16-bit arithmetic of the two kind::f16 modes (bf16x2 / f16x2), selected at compile time
+template <int kMode>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  if constexpr (kMode == PREC_FP16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+template <int kMode>
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  if constexpr (kMode == PREC_FP16) asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  else asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <int kMode>
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  if constexpr (kMode == PREC_FP16) asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  else asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <int kMode>
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  if constexpr (kMode == PREC_FP16) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  else asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+template <int kMode>
+__device__ __forceinline__ uint32_t htanh2(uint32_t a) {
+  uint32_t r;
+  if constexpr (kMode == PREC_FP16) asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a));
+  else asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(a));
+  return r;
+}
+// SiLU of a packed, halved and ACT-scaled pre-activation pair: h = ACT * x / 2 -> ACT * x * sigmoid(x) = h + h * tanh(h / ACT).
+// fp16: h / ACT may overflow to +-inf, for which MUFU.TANH returns +-1 -- exactly the saturated value.
+template <int kMode>
+__device__ __forceinline__ uint32_t hsilu2(uint32_t h2) {
+  uint32_t arg = h2;
+  if constexpr (kMode == PREC_FP16) arg = hmul2<kMode>(h2, 0x54005400u);  // x 64 = 1 / ACT (f16 64.0 = 0x5400)
+  const uint32_t t2 = htanh2<kMode>(arg);
+  return hfma2<kMode>(h2, t2, h2);
+}
+template <int kMode>
+__device__ __forceinline__ float h2_lo(uint32_t v) {
+  if constexpr (kMode == PREC_FP16) return __low2float(*reinterpret_cast<const __half2*>(&v));
+  else return __uint_as_float(v << 16);
+}
+template <int kMode>
+__device__ __forceinline__ float h2_hi(uint32_t v) {
+  if constexpr (kMode == PREC_FP16) return __high2float(*reinterpret_cast<const __half2*>(&v));
+  else return __uint_as_float(v & 0xffff0000u);
+}
+// bits of the 16-bit value 1.0 * ACT (the constant column that carries the folded bias of the second edge layer)
+template <int kMode>
+__device__ __forceinline__ constexpr uint32_t h_act_one_bits() { return kMode == PREC_FP16 ? 0x2400u : 0x3f80u; }
+template <int kMode>
+__device__ __forceinline__ void store_h(void* dst, float v) {
+  if constexpr (kMode == PREC_FP16) *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+  else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(v);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -250,7 +336,7 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int m, int n) {
 
 template <int kMode>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kMode == PREC_BF16) {
+  if constexpr (is16(kMode)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -338,11 +424,11 @@ __device__ __forceinline__ void op_store(uint8_t* base, int n_chunks, int grow, 
     const int kc = k / EPC, p = (k % EPC) / EPP;
     uint8_t* dst = base + ((size_t)mt * n_chunks + kc) * A_CHUNK_BYTES + sw128_offset(r, p);
     uint4 w;
-    if constexpr (kMode == PREC_BF16) {
-      w.x = pack_bf16x2(v[e + 0], v[e + 1]);
-      w.y = pack_bf16x2(v[e + 2], v[e + 3]);
-      w.z = pack_bf16x2(v[e + 4], v[e + 5]);
-      w.w = pack_bf16x2(v[e + 6], v[e + 7]);
+    if constexpr (is16(kMode)) {
+      w.x = pack_h2<kMode>(v[e + 0], v[e + 1]);
+      w.y = pack_h2<kMode>(v[e + 2], v[e + 3]);
+      w.z = pack_h2<kMode>(v[e + 4], v[e + 5]);
+      w.w = pack_h2<kMode>(v[e + 6], v[e + 7]);
     } else {
       w.x = f32_to_tf32(v[e + 0]);
       w.y = f32_to_tf32(v[e + 1]);
@@ -359,8 +445,8 @@ __device__ __forceinline__ void op_store1(uint8_t* base, int n_chunks, int grow,
   const int mt = grow >> 7, r = grow & 127;
   const int kc = k / EPC, within = k % EPC;
   uint8_t* dst = base + ((size_t)mt * n_chunks + kc) * A_CHUNK_BYTES + sw128_offset(r, within / EPP);
-  if constexpr (kMode == PREC_BF16) {
-    reinterpret_cast<__nv_bfloat16*>(dst)[within % EPP] = __float2bfloat16_rn(v);
+  if constexpr (is16(kMode)) {
+    store_h<kMode>(dst + 2 * (within % EPP), v);
   } else {
     reinterpret_cast<uint32_t*>(dst)[within % EPP] = f32_to_tf32(v);
   }

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(HP) k_egnn_prepare(const float* __restrict__ z
       for (int k = 0; k < IN_NF; ++k) acc = fmaf(w[k], hin[nl][k], acc);
     }
     h_res[hres_index(node, c, ldh)] = acc;
-    if constexpr (kMode != PREC_FP32_SIMT) op_store1<kMode>(h_op, op_chunks, node, c, acc);
+    if constexpr (kMode != PREC_FP32_SIMT) op_store1<kMode>(h_op, op_chunks, node, c, acc * op_scale(kMode));
   }
 }
 
@@ -409,9 +409,9 @@ __global__ void k_pack_weight(const PackArgs a) {
       v[e] = x * (a.scale != 0.f ? a.scale : 1.0f);
     }
     uint4 w;
-    if constexpr (kMode == PREC_BF16) {
-      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    if constexpr (is16(kMode)) {
+      w.x = pack_h2<kMode>(v[0], v[1]); w.y = pack_h2<kMode>(v[2], v[3]);
+      w.z = pack_h2<kMode>(v[4], v[5]); w.w = pack_h2<kMode>(v[6], v[7]);
     } else {
       w.x = f32_to_tf32(v[0]); w.y = f32_to_tf32(v[1]); w.z = f32_to_tf32(v[2]); w.w = f32_to_tf32(v[3]);
     }

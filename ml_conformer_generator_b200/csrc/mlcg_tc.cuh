@@ -40,6 +40,8 @@ struct GemmArgs {
   int out_op_chunks;
   float* resid;           // EPI_RESID_OP: fp32 residual stream, updated in place
   int ldr;
+  float out_scale;        // fp16 mode: power-of-two scale of the 16-bit outputs (P/Q rows, operand-format rows); see
+                          // mlcg_common.cuh "range management".  Ignored (1) in the other modes.
   int n_mtiles, n_ntiles; // tile grid (set by the launcher); the kernel is persistent and walks it with stride gridDim.x
   long long* prof;        // optional [grid][8] cycle counters (diagnostics): 0 producer waits for a free slot, 1 MMA issuer
                           // waits for operands, 2 MMA issuer waits for the epilogue, 3 epilogue waits for the accumulator,
@@ -68,7 +70,7 @@ constexpr int GEMM_THREADS = 64 + 128 * GEMM_NSUB;
 template <int kMode, int BN, int kEpi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
-  constexpr bool kFast = (kMode == PREC_BF16);
+  constexpr bool kFast = is16(kMode);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, TILE_M, Cfg::NPER);
+      constexpr uint32_t idesc = umma_idesc(umma_fmt(kMode), TILE_M, Cfg::NPER);
       uint32_t uses[Cfg::NSTAGE];
 #pragma unroll
       for (int s = 0; s < Cfg::NSTAGE; ++s) uses[s] = 0;
@@ -303,6 +305,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
             }
           }
         }
+        if constexpr (kMode == PREC_FP16) {  // range management: exact power-of-two scale of the 16-bit copy
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] *= p.out_scale;
+        }
         // pack into the 128-byte output block of this row
         const bool flush = (EPC == 32) || ((c0 & 32) != 0);
         if constexpr (EPC == 32) {
@@ -311,10 +317,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_tc_gemm(const GemmArgs p) {
         } else {
           if ((c0 & 32) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ow[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) ow[j] = pack_h2<kMode>(v[2 * j], v[2 * j + 1]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) ow[16 + j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            for (int j = 0; j < 16; ++j) ow[16 + j] = pack_h2<kMode>(v[2 * j], v[2 * j + 1]);
           }
         }
         if (flush) {
@@ -405,7 +411,7 @@ constexpr int EDGE_THREADS = 64 + EDGE_CT;  // warp 0 producer, warp 1 MMA, warp
 // W ring).  The second half of the selector area holds the carried partial sums of split targets.
 template <int kMode>
 struct EdgeSmemT {
-  static constexpr bool BF = (kMode == PREC_BF16);
+  static constexpr bool BF = is16(kMode);
   static constexpr int PQ_ESIZE = BF ? 2 : 4;                       // bytes per P/Q element
   static constexpr int PQ_PITCH = BF ? 912 : EDGE_QPITCH * 4;       // row pitch in bytes (== 16 mod 128: conflict-free)
   static constexpr int PQ_ROW = HP * PQ_ESIZE;                      // bytes copied per row
@@ -475,7 +481,7 @@ struct EdgeArgs {
 // between the two CTAs' shared memories.
 template <int kMode>
 __device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kMode == PREC_BF16) {
+  if constexpr (is16(kMode)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -499,7 +505,7 @@ __device__ __forceinline__ void umma_ss_bf16_pair(uint32_t d_tmem, uint64_t ades
 
 template <int kMode>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kMode == PREC_BF16) {
+  if constexpr (is16(kMode)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -527,11 +533,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 // trajectory: eps rel-L2 6.5e-3 instead of 1.6e-2; typical inputs: no measurable difference).
 template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_constant__ EdgeArgs p) {
-  constexpr bool kFast = (kMode == PREC_BF16);
+  constexpr bool kFast = is16(kMode);
   constexpr int EPC = epc(kMode);
-  constexpr int ELEMS = EPC / 4;  // K elements per thread per chunk (16 bf16 / 8 tf32) = 8 TMEM columns
-  constexpr bool kSegMma = (kMode == PREC_BF16) && !kEquiv;  // neighbour sum on the tensor core (bf16 mode)
-  constexpr bool kEarlyA = (kMode == PREC_BF16);  // first A chunks of tile t+1 are generated inside the epilogue of tile t
+  constexpr int ELEMS = EPC / 4;  // K elements per thread per chunk (16 bf16 / fp16, 8 tf32) = 8 TMEM columns
+  constexpr bool kSegMma = is16(kMode) && !kEquiv;  // neighbour sum on the tensor core (16-bit modes)
+  constexpr bool kEarlyA = is16(kMode);  // first A chunks of tile t+1 are generated inside the epilogue of tile t
+  constexpr float kDistScale = dist_scale(kMode);  // fp16: packed squared distances carry 2^-10 (inverse folded into wcd_h)
   using EdgeSmem = EdgeSmemT<kMode>;
   constexpr bool kPqBf16 = EdgeSmem::BF;
   extern __shared__ uint8_t smem_raw[];
@@ -611,7 +618,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) wv_s[i] = p.wv[i];
+  // gate / coordinate-head vector; the messages it multiplies carry ACT (fp16 mode), undone here exactly
+  for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) wv_s[i] = p.wv[i] * (1.0f / act_scale(kMode));
   if (warp == 1) {
     if constexpr (kPair) tmem_alloc_pair<512>(smem_u32(tmem_slot));
     else tmem_alloc<512>(smem_u32(tmem_slot));
@@ -690,7 +698,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
         }
     } else if (lane == 0) {
       constexpr int MM = kPair ? 2 * TILE_M : TILE_M;
-      constexpr uint32_t idesc = umma_idesc(kMode == PREC_BF16 ? 1 : 2, MM, 224);
+      constexpr uint32_t idesc = umma_idesc(umma_fmt(kMode), MM, 224);
       uint32_t wi = 0, ai = 0;
       for (int it = 0; it < n_iter; ++it) {
         if constexpr (kPair) mbar_wait(d_empty, (uint32_t)((it & 1) ^ 1));
@@ -741,7 +749,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // block; E (gated messages, bf16) is staged row-major = MN-major A operand, S is the 0/1 group selector.
           // Pair mode: M = 256 covers both CTAs' messages, N = 32 = [S of CTA 0 ; S of CTA 1]; CTA r uses D2 columns
           // 16r .. 16r+15.
-          constexpr uint32_t idesc2 = umma_idesc(1, MM, kPair ? 32 : 16) | (1u << 15);  // A is MN-major
+          constexpr uint32_t idesc2 = umma_idesc(umma_fmt(kMode), MM, kPair ? 32 : 16) | (1u << 15);  // A is MN-major
           constexpr int D2W = kPair ? 32 : 16;
           // all four channel blocks of the tile are staged (pass 1) and the gate-weighted selector is built: one batch
           mbar_wait(e_full(0), (uint32_t)(it & 1));
@@ -754,7 +762,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
               // results go to D columns cb*D2W.. : D is free (every warp arrived on e_full only after its pass 1) and the
               // next tile's MMAs cannot start before every warp has finished this tile's readout
               if constexpr (kPair) umma_ss_bf16_pair(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
-              else umma<PREC_BF16>(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
+              else umma<kMode>(tmem_base + cb * D2W, adesc, bdesc, idesc2, ks != 0);
             }
           }
           if constexpr (kPair) umma_commit_pair(e_done(0), 3);
@@ -832,7 +840,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
       const float2 rd = ri_d[r];
       const uint8_t* Prow = Ps + (info & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;  // invalid rows read row 0
       const uint8_t* Qrow = Qs + ((info >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
-      const uint32_t d2h = pack_bf16x2(rd.x, rd.x), d02h = pack_bf16x2(rd.y, rd.y);  // bf16 mode: packed distance features
+      // 16-bit modes: packed distance features (fp16: scaled by 2^-10 and clamped below the fp16 maximum)
+      auto pack_dist = [&](float d) {
+        const float ds = (kMode == PREC_FP16) ? fminf(d * kDistScale, 60000.0f) : d;
+        return pack_h2<kMode>(ds, ds);
+      };
+      const uint32_t d2h = pack_dist(rd.x), d02h = pack_dist(rd.y);
       if (!(kEarlyA && it > 0)) mbar_wait(pq_full, (uint32_t)(it & 1));  // (bf16: waited for during the previous tile)
       if (profiling) { long long c = clock64(); pacc[0] += c - c0; c0 = c; }  // row info + P/Q wait
 
@@ -856,24 +869,21 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
             const uint32_t wcp[4] = {c0.x, c0.y, c1.x, c1.y}, wdp[4] = {c0.z, c0.w, c1.z, c1.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              uint32_t h2, t2, a2;
-              asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(h2) : "r"(pa[i]), "r"(qa[i]));
+              uint32_t h2 = hadd2<kMode>(pa[i], qa[i]);
               if constexpr (kDistF32) {
                 const int k = k0 + e + 2 * i;
-                const float h_lo = fmaf(rd.y, p.wd[k], fmaf(rd.x, p.wc[k], __uint_as_float(h2 << 16)));
-                const float h_hi = fmaf(rd.y, p.wd[k + 1], fmaf(rd.x, p.wc[k + 1], __uint_as_float(h2 & 0xffff0000u)));
-                h2 = pack_bf16x2(h_lo, h_hi);
+                const float h_lo = fmaf(rd.y, p.wd[k], fmaf(rd.x, p.wc[k], h2_lo<kMode>(h2)));
+                const float h_hi = fmaf(rd.y, p.wd[k + 1], fmaf(rd.x, p.wc[k + 1], h2_hi<kMode>(h2)));
+                h2 = pack_h2<kMode>(h_lo, h_hi);
               } else {
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(h2) : "r"(d2h), "r"(wcp[i]));
-                asm("fma.rn.bf16x2 %0, %1, %2, %0;" : "+r"(h2) : "r"(d02h), "r"(wdp[i]));
+                h2 = hfma2<kMode>(d2h, wcp[i], h2);
+                h2 = hfma2<kMode>(d02h, wdp[i], h2);
               }
-              asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
-              asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(a2) : "r"(h2), "r"(t2));
-              w[(e >> 1) + i] = a2;
+              w[(e >> 1) + i] = hsilu2<kMode>(h2);
             }
           }
           // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416): low half of word 2
-          if (k0 == BIAS_COL - 4) w[2] = (w[2] & 0xffff0000u) | 0x3f80u;
+          if (k0 == BIAS_COL - 4) w[2] = (w[2] & 0xffff0000u) | h_act_one_bits<kMode>();
         } else {
           float wcv[ELEMS], wdv[ELEMS];  // 128-bit constant-bank loads (k0 is a multiple of 8)
 #pragma unroll
@@ -921,7 +931,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           const uint8_t* Qrow2 = Qs + ((info2 >> 8) & 0xff) * EdgeSmem::PQ_PITCH + qq * ELEMS * EdgeSmem::PQ_ESIZE;
           mbar_wait(pq_full, (uint32_t)((it + 1) & 1));
           for (int kc = 0; kc < min(EDGE_EARLY, p.n_kc); ++kc)
-            agen_chunk(kc, Prow2, Qrow2, rd2, pack_bf16x2(rd2.x, rd2.x), pack_bf16x2(rd2.y, rd2.y));
+            agen_chunk(kc, Prow2, Qrow2, rd2, pack_dist(rd2.x), pack_dist(rd2.y));
         }
       };
       // ---- A generation ----  (bf16: chunks 0 and 1 were generated during the previous tile's epilogue)
@@ -958,17 +968,31 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const float4 w4 = *reinterpret_cast<const float4*>(wv_s + col0 + e);
-            uint32_t h2, t2, m2a, m2b;
-            h2 = pack_bf16x2(v[e + 0], v[e + 1]);
-            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
-            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(m2a) : "r"(h2), "r"(t2));
-            h2 = pack_bf16x2(v[e + 2], v[e + 3]);
-            asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t2) : "r"(h2));
-            asm("fma.rn.bf16x2 %0, %1, %2, %1;" : "=r"(m2b) : "r"(h2), "r"(t2));
-            dotp[0] = fmaf(__uint_as_float(m2a << 16), w4.x, dotp[0]);
-            dotp[1] = fmaf(__uint_as_float(m2a & 0xffff0000u), w4.y, dotp[1]);
-            dotp[2] = fmaf(__uint_as_float(m2b << 16), w4.z, dotp[2]);
-            dotp[3] = fmaf(__uint_as_float(m2b & 0xffff0000u), w4.w, dotp[3]);
+            uint32_t m2a, m2b;
+            if constexpr (kMode == PREC_FP16) {
+              // fp16 mode: the accumulator is ACT * h (fp32); SiLU in fp32 -- tanh of the unscaled argument, the message
+              // stays ACT-scaled -- and ONE rounding when the pair is packed.  Same instruction count as the packed path.
+              float mm[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                float t;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v[e + u] * (1.0f / act_scale(kMode))));
+                mm[u] = fmaf(v[e + u], t, v[e + u]);
+              }
+              dotp[0] = fmaf(mm[0], w4.x, dotp[0]);
+              dotp[1] = fmaf(mm[1], w4.y, dotp[1]);
+              dotp[2] = fmaf(mm[2], w4.z, dotp[2]);
+              dotp[3] = fmaf(mm[3], w4.w, dotp[3]);
+              m2a = pack_h2<kMode>(mm[0], mm[1]);
+              m2b = pack_h2<kMode>(mm[2], mm[3]);
+            } else {
+              m2a = hsilu2<kMode>(pack_h2<kMode>(v[e + 0], v[e + 1]));
+              m2b = hsilu2<kMode>(pack_h2<kMode>(v[e + 2], v[e + 3]));
+              dotp[0] = fmaf(h2_lo<kMode>(m2a), w4.x, dotp[0]);
+              dotp[1] = fmaf(h2_hi<kMode>(m2a), w4.y, dotp[1]);
+              dotp[2] = fmaf(h2_lo<kMode>(m2b), w4.z, dotp[2]);
+              dotp[3] = fmaf(h2_hi<kMode>(m2b), w4.w, dotp[3]);
+            }
             if constexpr (kSegMma) {
               mw[(e >> 1)] = m2a;
               mw[(e >> 1) + 1] = m2b;
@@ -1080,7 +1104,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
                   if (carried_in(g)) val = carry_rd[ch] + val;
                   if (carried_out(g)) carry_wr[ch] = val;
                   else if (fx >= 0) atomicAdd(p.fix_agg + (size_t)fx * HP + ch, val);
-                  else *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(val * 0.01f);
+                  else store_h<kMode>(dst, val * agg_out_scale(kMode));
                 }
               }
             }
@@ -1096,7 +1120,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
               const int k = piece * 8 + 2 * e;
               const float g0 = (k >= lo_k && k < hi_k) ? gates[k] : 0.f;
               const float g1 = (k + 1 >= lo_k && k + 1 < hi_k) ? gates[k + 1] : 0.f;
-              w[e] = pack_bf16x2(g0, g1);
+              w[e] = pack_h2<kMode>(g0, g1);
             }
             *reinterpret_cast<uint4*>(gbase + EdgeSmem::SEL_OFF + (piece >> 3) * 2048 + sw128_offset(g, piece & 7)) =
                 make_uint4(w[0], w[1], w[2], w[3]);
@@ -1215,7 +1239,7 @@ __global__ void k_edge_fixup(const int* __restrict__ fix_node, int n_fix, float*
       v[e] = x.x; v[e + 1] = x.y; v[e + 2] = x.z; v[e + 3] = x.w;
     }
 #pragma unroll
-    for (int e = 0; e < EPP; ++e) v[e] = (kMode == PREC_BF16) ? v[e] * 0.01f : v[e] / 100.0f;
+    for (int e = 0; e < EPP; ++e) v[e] = is16(kMode) ? v[e] * agg_out_scale(kMode) : v[e] / 100.0f;
     op_store<kMode, EPP>(agg_op, agg_chunks, node, pc * EPP, v);
   }
 }

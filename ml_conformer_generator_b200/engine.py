@@ -9,7 +9,7 @@ import torch
 from . import _lib
 from .schedule import all_step_scalars, decode_scalars, forward_level_scalars, gamma_table
 
-PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 
 
 class MlcgError(RuntimeError):
@@ -209,6 +209,46 @@ class Engine:
                                                self._stream()), "seer_forward")
         self._keep = [el, dist, adj]
         return logits, bonds
+
+    # ------------------------------------------------------------------------------------------------------------
+    # inertial fragment matching on the device (reference utils/mol_utils.py:373-550)
+    def ifm_context(self, fixed_fragment_x: torch.Tensor, reference_context: torch.Tensor, context_norms: Dict,
+                    n_nodes: torch.Tensor):
+        """Device version of ifm_prepare_gen_fragment_context after its batch-independent prologue.  n_nodes: (B) total
+        atoms per sample.  Returns device tensors (ctx (B,3) normalised, shift (B,3), rotation (B,3,3), n_gen (B) i32)."""
+        from .mol_utils import get_moment_of_inertia_tensor
+        ffx = fixed_fragment_x.detach().to("cpu", torch.float32)
+        n_ff = int(ffx.size(0))
+        moi0 = (torch.diag(torch.as_tensor(reference_context, dtype=torch.float32).cpu())
+                - get_moment_of_inertia_tensor(ffx, torch.ones(n_ff))).contiguous()
+        com = (n_ff * ffx.mean(dim=0)).to(torch.float32).contiguous()
+        mean = torch.as_tensor(context_norms["mean"], dtype=torch.float32).contiguous()
+        mad = torch.as_tensor(context_norms["mad"], dtype=torch.float32).contiguous()
+        nn = n_nodes.to(self.device, torch.int32).contiguous()
+        B = int(nn.numel())
+        ctx = torch.empty(B, 3, device=self.device)
+        shift = torch.empty(B, 3, device=self.device)
+        rot = torch.empty(B, 3, 3, device=self.device)
+        n_gen = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.mlcg_ifm_context(self.h, _ptr(moi0), _ptr(com), n_ff, _ptr(mean), _ptr(mad), _ptr(nn), B,
+                                              _ptr(ctx), _ptr(shift), _ptr(rot), _ptr(n_gen), self._stream()), "ifm_context")
+        return ctx, shift, rot, n_gen
+
+    def ifm_merge_inputs(self, x_gen: torch.Tensor, cls_gen: torch.Tensor, shift: torch.Tensor, rot: torch.Tensor,
+                         fixed_fragment_x: torch.Tensor, fixed_fragment_h: torch.Tensor, max_n_nodes: int):
+        """Device version of inverse_coord_transform + ifm_prepare_fragments_for_merge: (z_known (B,N,11), fixed_mask (B,N))."""
+        x_gen = x_gen.to(self.device, torch.float32).contiguous()
+        cls_gen = cls_gen.to(self.device, torch.int32).contiguous()
+        ffx = fixed_fragment_x.to(self.device, torch.float32).contiguous()
+        ffh = fixed_fragment_h.to(self.device, torch.float32).contiguous()
+        B, Ng = int(x_gen.shape[0]), int(x_gen.shape[1])
+        zk = torch.empty(B, max_n_nodes, 11, device=self.device)
+        fm = torch.empty(B, max_n_nodes, device=self.device)
+        self._check(self.lib.mlcg_ifm_merge_inputs(self.h, _ptr(x_gen), _ptr(cls_gen), _ptr(shift.contiguous()),
+                                                   _ptr(rot.contiguous()), _ptr(ffx), _ptr(ffh), int(ffx.shape[0]), B, Ng,
+                                                   int(max_n_nodes), _ptr(zk), _ptr(fm), self._stream()), "ifm_merge_inputs")
+        self._keep = [x_gen, cls_gen, ffx, ffh, shift, rot]
+        return zk, fm
 
     def generate_host(self, n_nodes: np.ndarray, max_n_nodes: int, ctx: np.ndarray, T: int = 100,
                       resample_steps: int = 0, seed: int = 0, sample_offset: int = 0, out=None, sample_ids=None,

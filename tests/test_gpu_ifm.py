@@ -1,0 +1,84 @@
+"""GPU: inertial fragment matching on the device (mlcg_ifm_context / mlcg_ifm_merge_inputs) against the reference's own
+outputs (tests/golden/host_utils.npz, produced by utils/mol_utils.py:373-550 of the reference), and the default fragment
+mode of the public API running both reverse loops without a host round trip."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from ml_conformer_generator_b200.config import CONTEXT_NORMS
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ifm_context_against_reference_golden(engines):
+    g = golden("host_utils")
+    e = engines("fp32")
+    n_nodes = torch.from_numpy(g["ifm_n_nodes"])
+    ctx, shift, rot, n_gen = e.ifm_context(torch.from_numpy(g["ifm_ff_x"]), torch.from_numpy(g["yibfeu_context"]),
+                                           CONTEXT_NORMS, n_nodes)
+    n_ff = g["ifm_ff_x"].shape[0]
+    assert torch.equal(n_gen.cpu().long(), n_nodes.long() - n_ff)
+    assert float((shift.cpu() - torch.from_numpy(g["ifm_shift"])).abs().max()) < 1e-6
+    ref_ctx = torch.from_numpy(g["ifm_context"])[:, 0, :]       # (B, n_max_frag, 3) masked broadcast -> row 0
+    assert float((ctx.cpu() - ref_ctx).abs().max()) < 2e-5
+    # eigenvectors: the reference's columns up to the solver's sign choice; orthonormal; largest component positive
+    R, Rref = rot.cpu().double(), torch.from_numpy(g["ifm_rotation"]).double()
+    for b in range(R.shape[0]):
+        for c in range(3):
+            d = min(float((R[b, :, c] - Rref[b, :, c]).abs().max()), float((R[b, :, c] + Rref[b, :, c]).abs().max()))
+            assert d < 1e-4
+            assert float(R[b, R[b, :, c].abs().argmax(), c]) > 0
+        assert float((R[b].t() @ R[b] - torch.eye(3, dtype=torch.double)).abs().max()) < 1e-6
+
+
+def test_ifm_merge_inputs_against_reference_golden(engines):
+    g = golden("host_utils")
+    e = engines("fp32")
+    xg, hg = torch.from_numpy(g["ifm_xg"]), torch.from_numpy(g["ifm_hg"])
+    cls = hg.argmax(-1).int()
+    ff_x, ff_h = torch.from_numpy(g["ifm_ff_x"]), torch.from_numpy(g["ifm_ff_h"]).float()
+    # with the reference's own rotation / shift the merge inputs must equal the reference's z_known / fixed_mask
+    zk, fm = e.ifm_merge_inputs(xg, cls, torch.from_numpy(g["ifm_shift"]).cuda(), torch.from_numpy(g["ifm_rotation"]).cuda(),
+                                ff_x, ff_h, 25)
+    assert float((zk.cpu() - torch.from_numpy(g["ifm_z_known"])).abs().max()) < 2e-6
+    assert torch.equal(fm.cpu().unsqueeze(-1), torch.from_numpy(g["ifm_fixed_mask"]))
+    # with the device eigen-decomposition: same construction on the device rotation (x R^T - shift)
+    ctx, shift, rot, _ = e.ifm_context(ff_x, torch.from_numpy(g["yibfeu_context"]), CONTEXT_NORMS, torch.from_numpy(g["ifm_n_nodes"]))
+    zk2, _ = e.ifm_merge_inputs(xg, cls, shift, rot, ff_x, ff_h, 25)
+    n_ff = ff_x.shape[0]
+    want = torch.bmm(xg, rot.cpu().transpose(1, 2)) - shift.cpu().view(-1, 1, 3)
+    assert float((zk2.cpu()[:, n_ff:, :3] - want).abs().max()) < 2e-6
+    assert torch.equal(zk2.cpu()[:, n_ff:, 3:], hg.float())
+    assert float((zk2.cpu()[:, :n_ff, :3] - ff_x).abs().max()) == 0.0
+    # padded generated rows: zero input row -> -shift, empty one-hot (as the reference)
+    xg0 = xg.clone()
+    xg0[:, -2:] = 0
+    cls0 = cls.clone()
+    cls0[:, -2:] = -1
+    zk3, _ = e.ifm_merge_inputs(xg0, cls0, shift, rot, ff_x, ff_h, 25)
+    assert float((zk3.cpu()[:, -2:, :3] + shift.cpu().view(-1, 1, 3)).abs().max()) < 1e-6
+    assert float(zk3.cpu()[:, -2:, 3:].abs().max()) == 0.0
+
+
+def test_default_fragment_mode_end_to_end(state_dicts):
+    """generate_tensors with a fixed fragment and inertial_fragment_matching=True (the reference's default fragment mode):
+    two device loops with the IFM math between them on the device; the fixed atoms come out with the fragment's classes
+    and the fragment's internal geometry."""
+    from ml_conformer_generator_b200 import MLConformerGenerator
+    g = golden("host_utils")
+    gen = MLConformerGenerator(diffusion_steps=8, device=torch.device("cuda:0"), precision="fp16",
+                               edm_state_dict=state_dicts[0], adj_mat_seer_state_dict=state_dicts[1])
+    ff_x, ff_h = torch.from_numpy(g["ifm_ff_x"]), torch.from_numpy(g["ifm_ff_h"]).float()
+    out = gen.generate_tensors(torch.from_numpy(g["yibfeu_context"]), n_atoms=23, n_samples=6, variance=2,
+                               fixed_fragment=(ff_x, ff_h), inertial_fragment_matching=True, ifm_diffusion_level=4)
+    x, cls, n_nodes = out["x"].cpu(), out["atom_class"].cpu(), out["n_nodes"]
+    n_ff = ff_x.shape[0]
+    assert x.shape == (6, 25, 3) and torch.isfinite(x).all()
+    assert bool((cls[:, :n_ff].long() == ff_h.argmax(-1).view(1, -1)).all())
+    for b in range(6):
+        assert bool((cls[b, : n_nodes[b]] >= 0).all()) and bool((cls[b, n_nodes[b]:] == -1).all())
+        # the fragment is re-injected at every step: its internal distances survive up to the final decode noise
+        d = torch.cdist(x[b, :n_ff], x[b, :n_ff])
+        assert float((d - torch.cdist(ff_x, ff_x)).abs().max()) < 0.2
+    gen.engine.close()

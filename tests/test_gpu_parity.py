@@ -14,7 +14,7 @@ from ml_conformer_generator_b200.config import CONTEXT_NORMS
 from oracle import edm_oracle as O
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 2e-2}
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "fp16": 1e-3, "bf16": 2e-2}
 
 
 def _norm_ctx(raw, B):
@@ -22,7 +22,7 @@ def _norm_ctx(raw, B):
     return c.view(1, 3).repeat(B, 1)
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("shape", [(300, 896, 448, 448), (129, 448, 896, 448), (260, 512, 64, 256), (128, 256, 2048, 256)])
 def test_tc_gemm(engines, mode, shape):
     M, N, K, bn = shape
@@ -32,10 +32,10 @@ def test_tc_gemm(engines, mode, shape):
     b = torch.randn(N, generator=g)
     c = engines(mode).test_gemm(mode, bn, a, w, b).cpu()
     ref = a.double() @ w.double().t() + b.double()
-    assert rel_l2(c, ref) < (2e-3 if mode == "tf32" else 1e-2)
+    assert rel_l2(c, ref) < (1e-2 if mode == "bf16" else 2e-3)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["egnn_small", "egnn_n39"])
 def test_egnn_forward_golden(engines, mode, name):
     g = golden(name)
@@ -52,7 +52,7 @@ def test_egnn_forward_golden(engines, mode, name):
     assert float((eps[:, :, :3] * nm).sum(1).abs().max()) < 1e-3 * float(eps[:, :, :3].abs().max())
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16", "bf16"])
 def test_teacher_forced_trajectory(engines, mode):
     """Per-step eps on the reference's own z_t trajectory (11 denoiser calls of a T=10 run)."""
     g = golden("edm_forward_T10")
@@ -263,7 +263,7 @@ def test_seer_inputs_against_oracle(engines):
     assert float((adj.cpu() != adj_r).float().mean()) < 1e-3
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "fp16", "bf16"])
 def test_modes_agree_at_full_width(engines, mode):
     """N = 39 molecules (13 edge tiles each) and ragged sizes: tensor-core modes against the exact-fp32 CUDA mode."""
     g = torch.Generator().manual_seed(21)
@@ -315,7 +315,7 @@ def test_argument_errors(engines):
         e.egnn_forward(torch.zeros(3), torch.zeros(3, 16, 11), torch.zeros(3, 3))
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "fp16", "bf16"])
 def test_every_molecule_size_against_fp32_cuda(engines, mode):
     """All sizes 1..39 in one batch (twice, shuffled): exercises whole-target tiles (n < 13), split-target tiles with and
     without a target cut at the tile boundary, single-tile molecules and the n = 1 / n = 2 corner cases, against the exact
@@ -343,4 +343,4 @@ def test_every_molecule_size_against_fp32_cuda(engines, mode):
         worst = max(worst, rel_l2(out[mode][b, :n], ref))
         assert float(out[mode][b, n:].abs().max()) == 0.0 if n < N else True
     print("all sizes 1..39,", mode, "worst per-molecule rel-L2 vs fp32 CUDA:", worst)
-    assert worst < (2e-3 if mode == "tf32" else 3e-2)
+    assert worst < (3e-2 if mode == "bf16" else 2e-3)

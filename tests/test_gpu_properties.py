@@ -16,7 +16,7 @@ from ml_conformer_generator_b200.config import CONTEXT_NORMS
 from oracle import edm_oracle as O
 
 pytestmark = pytest.mark.gpu
-EQ_TOL = {"fp32": 1e-4, "tf32": 2e-3, "bf16": 2e-2}
+EQ_TOL = {"fp32": 1e-4, "tf32": 2e-3, "fp16": 2e-3, "bf16": 2e-2}
 
 
 def _batch(B, seed, n_max=39):
@@ -38,7 +38,7 @@ def _rotation(seed):
     return q
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "fp16", "bf16"])
 def test_padding_and_batch_invariance(engines, mode):
     e = engines(mode)
     n_nodes, nm, z, ctx, t = _batch(300, 1)
@@ -55,7 +55,7 @@ def test_padding_and_batch_invariance(engines, mode):
     assert torch.equal(sub, full[idx, :n_max])
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16", "bf16"])
 def test_rotation_translation_permutation_equivariance(engines, mode):
     e = engines(mode)
     B = 64 if mode == "fp32" else 256
@@ -166,7 +166,7 @@ def test_gemm_phase_profile_is_consistent(engines):
         assert p["epi_wait_accumulator"] + p["epilogue"] < 1.5 * p["cta_lifetime"] + 5000
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["tf32", "fp16", "bf16"])
 def test_forward_is_bitwise_reproducible(engines, mode):
     """Repeated launches on the same inputs give bit-identical eps (fixed reduction orders; the split-target side buffer
     sees exactly two commutative addends), also after the batch plan has been rebuilt."""
