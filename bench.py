@@ -2,7 +2,7 @@
 """Headline benchmark: generated molecules / second through the hot path (T=100 reverse steps = 101 EGNN forwards,
 then GCN-input build + AdjMatSeer + bond argmax), one process per GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|tf32] [--workload C3|C2|C1|C4|C5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp16|bf16|tf32] [--workload C3|C2|C1|C4|C5]
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...      (N > 1)
   python bench.py --impl reference ...        (the reference's own torch CPU path on the host cores)
 
@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp16"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "tf32"])
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip parity / breakdown / secondary workload")

@@ -861,6 +861,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
           // A-operand word.  wc / wd come from the constant bank as packed bf16x2 (warp-uniform index).
 #pragma unroll
           for (int e = 0; e < ELEMS; e += 8) {
+            // K columns >= 424 are padding of the 420 (+ bias column) real ones: their weights are zero and so is the
+            // activation (P = Q = 0 there); skip the loads and the MUFU work (warp-uniform: 1.5 of the last chunk's 4 quarters)
+            if (k0 + e >= 424) {
+              w[(e >> 1) + 0] = w[(e >> 1) + 1] = w[(e >> 1) + 2] = w[(e >> 1) + 3] = 0u;
+              continue;
+            }
             const uint4 pw = *reinterpret_cast<const uint4*>(Prow + (kc * EPC + e) * 2);
             const uint4 qw = *reinterpret_cast<const uint4*>(Qrow + (kc * EPC + e) * 2);
             const uint4 c0 = *reinterpret_cast<const uint4*>(&p.wcd_h[(k0 + e)]);      // channels k0+e .. +3: wc, wc, wd, wd

@@ -23,7 +23,7 @@ def _ptr(t: Optional[torch.Tensor]):
 class Engine:
     """One handle on one CUDA device.  Not thread-safe."""
 
-    def __init__(self, device: torch.device = torch.device("cuda:0"), precision: str = "bf16"):
+    def __init__(self, device: torch.device = torch.device("cuda:0"), precision: str = "fp16"):
         device = torch.device(device)
         if device.type != "cuda":
             raise MlcgError("ml_conformer_generator_b200 runs on sm_100 CUDA devices only (got %s); there is no CPU "

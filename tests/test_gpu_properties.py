@@ -178,3 +178,23 @@ def test_forward_is_bitwise_reproducible(engines, mode):
     e.set_batch(n_nodes.numpy(), 39)
     c = e.egnn_forward(t, z, ctx)
     assert torch.equal(a, b) and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("mode", ["fp16", "bf16", "tf32"])
+def test_forward_bitwise_stress(engines, mode):
+    """Race hunt by repetition: 400 forwards per mode (27 edge-kernel launches each, i.e. > 10 000 launches of the fused
+    kernel with early A generation, carried split targets and the side-buffer path active) on a ragged batch must all be
+    bit-identical -- any unordered access between the bulk-copy producer, the tensor core and the compute warps would
+    show up as a differing bit sooner or later.  Complements compute-sanitizer (profiles/r2_sanitizer.txt), whose
+    racecheck cannot see the async proxy."""
+    e = engines(mode)
+    n_nodes, nm, z, ctx, t = _batch(300, 17)
+    e.set_batch(n_nodes.numpy(), 39)
+    ref = e.egnn_forward(t, z, ctx).clone()
+    zd, td, cd = z.cuda(), t.cuda(), ctx.cuda()
+    bad = 0
+    for it in range(400):
+        out = e.egnn_forward(td, zd, cd)
+        if it % 8 == 7 or it == 399:  # compare on the device, sync rarely so launches queue back to back
+            bad += int(not torch.equal(out, ref))
+    assert bad == 0
