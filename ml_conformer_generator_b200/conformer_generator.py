@@ -171,7 +171,15 @@ class MLConformerGenerator:
     def generate_tensors(self, reference_context: torch.Tensor, n_atoms: int, n_samples: int = 10, variance: int = 2,
                          resample_steps: int = 0, **fragment_kwargs) -> Dict[str, torch.Tensor]:
         """The accelerated part of generate_conformers end to end: EDM samples -> GCN inputs (declared connectivity
-        rule) -> AdjMatSeer -> bond orders.  Returns device tensors."""
+        rule) -> AdjMatSeer -> bond orders.  Returns device tensors.
+
+        PROVISIONAL `bonds` / `bond_logits`: coordinates and atom classes are the reference's (parity-tested), and
+        AdjMatSeer itself is parity-tested on identical tensor inputs, but the inputs built here are NOT the ones the
+        reference builds: it takes the 1st-order connectivity from RDKit's rdDetermineBonds.DetermineConnectivity and
+        renumbers the atoms into SMILES output order (utils/mol_utils.py:110-126, 146-194) before the slot-dependent GCN
+        (nodes_coord_fc couples the 42 slots); this path uses d <= 1.3 (Rcov_i + Rcov_j) and keeps generation order.  The
+        bond orders a trained model gives for the same sample can therefore differ.  `generate_conformers` (RDKit
+        canonicalisation, then AdjMatSeerB200) is the parity path for bonds."""
         x, h, node_mask = self.edm_sample_tensors(reference_context, n_samples, n_atoms + variance, n_atoms - variance,
                                                   resample_steps, **fragment_kwargs)
         n_nodes = node_mask.sum(dim=(1, 2)).long()
@@ -185,7 +193,8 @@ class MLConformerGenerator:
     def generate_sdf(self, reference_context: torch.Tensor, n_atoms: int, n_samples: int = 10, variance: int = 2,
                      resample_steps: int = 0, **fragment_kwargs) -> List[str]:
         """generate_tensors + an RDKit-free V2000 writer: one mol block per sample with the GCN's bond orders.  No
-        sanitisation / hydrogens / MMFF (those are RDKit's, reference conformer_generator.py:357-368)."""
+        sanitisation / hydrogens / MMFF (those are RDKit's, reference conformer_generator.py:357-368).  The bond orders
+        are PROVISIONAL (see generate_tensors); every block says so in its comment line."""
         from .mol_utils import samples_to_sdf_blocks
         t = self.generate_tensors(reference_context, n_atoms, n_samples, variance, resample_steps, **fragment_kwargs)
         return samples_to_sdf_blocks(t["x"], t["atom_class"], t["bonds"], t["n_nodes"])

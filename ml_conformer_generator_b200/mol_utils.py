@@ -238,14 +238,21 @@ def bond_orders_from_logits(logits: torch.Tensor) -> torch.Tensor:
     return torch.tril(order, diagonal=-1)
 
 
+PROVISIONAL_BONDS_NOTE = ("bond orders PROVISIONAL: AdjMatSeer fed with distance-rule connectivity in generation order, "
+                          "not RDKit DetermineConnectivity + SMILES-order atoms")
+
+
 def samples_to_sdf_blocks(x: torch.Tensor, atom_class: torch.Tensor, bonds: torch.Tensor, n_nodes: torch.Tensor,
-                          names: Optional[Sequence[str]] = None) -> List[str]:
+                          names: Optional[Sequence[str]] = None, comment: str = PROVISIONAL_BONDS_NOTE) -> List[str]:
     """V2000 mol blocks ("...M  END\n$$$$\n") from the accelerated path's tensors, without RDKit.
 
     x (B,N,3) coordinates, atom_class (B,N) (-1 = padding), bonds (B,D,D) bond order per pair as mlcg_seer_forward /
     bond_orders_from_logits return it (only i > j is read; 1 single, 2 double, 3 triple, 4 aromatic -- the reference's
     bond_type_dict, mol_utils.py:10-15).  This is the wire format of the reference's results (Chem.MolToMolBlock in
-    cheminformatics/pipeline.py:88) minus RDKit's sanitisation: no implicit hydrogens, no charge / valence fix-up."""
+    cheminformatics/pipeline.py:88) minus RDKit's sanitisation: no implicit hydrogens, no charge / valence fix-up.
+    `comment` goes to the block's comment line (line 3): by default it marks the bond orders of the RDKit-free path as
+    provisional -- AdjMatSeer is slot-dependent and the reference feeds it RDKit connectivity with atoms renumbered into
+    SMILES output order (utils/mol_utils.py:110-126, 146-194), which cannot be reproduced without RDKit."""
     x = x.detach().cpu()
     cls = atom_class.detach().cpu()
     bo = bonds.detach().cpu()
@@ -255,7 +262,7 @@ def samples_to_sdf_blocks(x: torch.Tensor, atom_class: torch.Tensor, bonds: torc
         if n > 999:
             raise ValueError("V2000 mol blocks hold at most 999 atoms")
         pairs = [(i, j, int(bo[b, i, j])) for i in range(n) for j in range(i) if int(bo[b, i, j]) != 0]
-        lines = [names[b] if names is not None else "mlcg_%d" % b, "  ml_conformer_generator_b200", "",
+        lines = [names[b] if names is not None else "mlcg_%d" % b, "  ml_conformer_generator_b200", comment[:200],
                  "%3d%3d  0  0  0  0  0  0  0  0999 V2000" % (n, len(pairs))]
         for i in range(n):
             lines.append("%10.4f%10.4f%10.4f %-3s 0  0  0  0  0  0  0  0  0  0  0  0"
