@@ -155,7 +155,8 @@ def reference_modules(device):
     dyn = EGNNDynamics(in_node_nf=9, context_node_nf=3, hidden_nf=420, device=torch.device(device))  # conformer_generator.py:67-72
     edm = EquivariantDiffusion(dynamics=dyn, in_node_nf=8, timesteps=1000, noise_precision=1e-5)
     edm.load_state_dict(sd, strict=True)
-    seer = AdjMatSeer(dimension=42, n_hidden=2048, embedding_dim=64, num_embeddings=36, num_bond_types=5)
+    seer = AdjMatSeer(dimension=42, n_hidden=2048, embedding_dim=64, num_embeddings=36, num_bond_types=5,
+                      device=torch.device(device))  # conformer_generator.py:81-88
     seer.load_state_dict(ssd, strict=True)
     edm.gamma = PredefinedNoiseSchedule(timesteps=T_STEPS, precision=1e-5)  # conformer_generator.py:104-113
     edm.time_steps = torch.flip(torch.arange(0, T_STEPS), dims=[0])

@@ -10,3 +10,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k "regex:k_s
 timeout 900 ncu --set full --clock-control none -k "regex:k_tc_gemm<1, 256" -s 2 -c 3 -o gpurun_out/r2_gcn_gemm python tools/small_kernels_case.py > gpurun_out/ncu_gcn.log 2>&1; echo "gcn rc=$?"
 timeout 600 compute-sanitizer --tool memcheck python tools/sanitizer_case.py fp16,bf16,tf32 4 > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/memcheck.log
 timeout 700 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/sanitizer_case.py fp16,tf32 1 > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -5 gpurun_out/racecheck.log
+timeout 600 python bench.py --impl reference --ref-device cuda --steps 3 --warmup 1 > gpurun_out/bench_reference_gpu.json 2> gpurun_out/bench_reference_gpu.err; echo "refgpu rc=$?"; tail -c 300 gpurun_out/bench_reference_gpu.err
+timeout 600 python bench.py --workload C1 --steps 3 --warmup 2 --no-extras > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "c1 rc=$?"
+timeout 900 python bench.py --impl reference --workload C1 --ref-full --ref-mols 20 --steps 1 --warmup 0 > gpurun_out/bench_reference_c1_full.json 2> gpurun_out/bench_reference_c1_full.err; echo "ref c1 rc=$?"
