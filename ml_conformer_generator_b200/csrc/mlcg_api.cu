@@ -167,11 +167,11 @@ static cudaError_t launch_gemm_mode(int mode, const GemmArgs& a, int n_mtiles, i
   return mode == PREC_BF16 ? launch_gemm<PREC_BF16, BN, kEpi>(a, n_mtiles, n_ntiles, st)
                            : launch_gemm<PREC_TF32, BN, kEpi>(a, n_mtiles, n_ntiles, st);
 }
-template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false>
+template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false, bool kProf = false>
 static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv, kPair, kDistF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_tc_edge<kMode, kEquiv, kPair, kDistF32, kProf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          EdgeSmemT<kMode>::ALLOC);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -188,7 +188,7 @@ static cudaError_t launch_edge(const EdgeArgs& a, int grid, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair, kDistF32>, a);
+  return cudaLaunchKernelEx(&cfg, k_tc_edge<kMode, kEquiv, kPair, kDistF32, kProf>, a);
 }
 // Edge tiles are 128-row ranges of a molecule's edge list that may split a target node's neighbours over two tiles
 // (default); MLCG_EDGE_SPLIT=0 keeps whole targets per tile (lower row occupancy, no fix-up kernel).
@@ -249,9 +249,18 @@ static void edge_tile_owner(int num_sms, int n_tiles, std::vector<int>& owner) {
     }
   }
 }
-static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st) {
+static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st, bool prof = false) {
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
+  if (prof) {
+    // instrumented instantiations exist for the default variant of each mode only (CTA pairs, default distance terms)
+    if (!pair || edge_dist_fp32(mode) != (mode == PREC_FP16)) return cudaErrorNotSupported;
+    if (mode == PREC_FP16)
+      return equiv ? launch_edge<PREC_FP16, true, true, true, true>(a, grid, st) : launch_edge<PREC_FP16, false, true, true, true>(a, grid, st);
+    if (mode == PREC_BF16)
+      return equiv ? launch_edge<PREC_BF16, true, true, false, true>(a, grid, st) : launch_edge<PREC_BF16, false, true, false, true>(a, grid, st);
+    return equiv ? launch_edge<PREC_TF32, true, true, false, true>(a, grid, st) : launch_edge<PREC_TF32, false, true, false, true>(a, grid, st);
+  }
   if (mode == PREC_FP16 && edge_dist_fp32(mode)) {
     if (pair)
       return equiv ? launch_edge<PREC_FP16, true, true, true>(a, grid, st) : launch_edge<PREC_FP16, false, true, true>(a, grid, st);
@@ -1345,7 +1354,7 @@ extern "C" int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, v
   CK(buf.ensure((size_t)grid_e * 16 * sizeof(long long)));
   EdgeArgs ea = edge_args(h, L, h->xa.as<float>(), h->xb.as<float>());
   ea.prof = buf.as<long long>();
-  CK(launch_edge_mode(h->precision, L.equiv, ea, grid_e, st));
+  CK(launch_edge_mode(h->precision, L.equiv, ea, grid_e, st, true));
   h->launches++;
   CK(launch_edge_fixup(h, h->precision, L.equiv, ea, st));
   std::vector<long long> host((size_t)grid_e * 16);

@@ -531,7 +531,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 // kDistF32 (bf16 mode only): evaluate the two distance terms of the first layer in fp32 instead of packed bf16x2.  About 8 %
 // slower; only matters when d2 * wc dominates the pre-activation (worst teacher-forced step of the random-weight
 // trajectory: eps rel-L2 6.5e-3 instead of 1.6e-2; typical inputs: no measurable difference).
-template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false>
+// kProf: build the phase cycle counters in (mlcg_edge_phase_profile).  The production instantiations carry none of it: even
+// predicated off, the counter code costs ~15 % of the issue slots of the A-generation loop.
+template <int kMode, bool kEquiv, bool kPair, bool kDistF32 = false, bool kProf = false>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_constant__ EdgeArgs p) {
   constexpr bool kFast = is16(kMode);
   constexpr int EPC = epc(kMode);
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge(const __grid_consta
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t ai = 0;
     long long* pacc = reinterpret_cast<long long*>(gbase + EdgeSmem::PROF_OFF);  // only thread ct == 0 touches it
-    const bool profiling = (p.prof != nullptr) && (ct == 0);
+    const bool profiling = kProf && (p.prof != nullptr) && (ct == 0);
     if (profiling)
       for (int k = 0; k < 16; ++k) pacc[k] = 0;
     // Row metadata (d2, d0^2, group / neighbour ids, unit vectors) and the group selector of a tile are double-buffered:
