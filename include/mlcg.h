@@ -209,6 +209,12 @@ int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_ref, const f
 int mlcg_plan_edge_tiles(const int32_t* n_nodes_host, int B, int N, int num_sms, int32_t* tiles_out, int32_t* owner_out,
                          int max_tiles, int32_t* n_fix_out);
 
+/* 1 if any mlcg_decode since the last call produced a non-finite coordinate, else 0; clears the flag; synchronises `stream`.
+ * A trajectory can diverge (random-init weights in inpaint mode do, in every precision -- the reference's own fp32 path goes
+ * NaN too); in MLCG_PREC_FP16 it also happens when pairwise distances exceed ~1.6e4 (pre-activations leave the fp16 range;
+ * ordinary molecules stay below 1e2).  The Python host turns this into a RuntimeWarning. */
+int mlcg_nonfinite(mlcg_handle* h, void* stream);
+
 /* Introspection for benches / tests. */
 int mlcg_num_edge_tiles(mlcg_handle* h);
 int64_t mlcg_num_edges(mlcg_handle* h);          /* sum_b n_b (n_b - 1) */

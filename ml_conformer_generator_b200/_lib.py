@@ -19,7 +19,7 @@ EXPORTS = [
     "mlcg_decode", "mlcg_sample", "mlcg_seer_inputs", "mlcg_seer_forward", "mlcg_generate", "mlcg_num_edge_tiles",
     "mlcg_num_edges", "mlcg_kernel_launches", "mlcg_time_edge_kernel", "mlcg_edge_phase_profile", "mlcg_test_gemm",
     "mlcg_shape_moments", "mlcg_shape_tanimoto", "mlcg_gemm_phase_profile", "mlcg_plan_edge_tiles",
-    "mlcg_egnn_forward_breakdown", "mlcg_ifm_context", "mlcg_ifm_merge_inputs",
+    "mlcg_egnn_forward_breakdown", "mlcg_ifm_context", "mlcg_ifm_merge_inputs", "mlcg_nonfinite",
 ]
 
 
@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.mlcg_seer_forward.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     lib.mlcg_generate.argtypes = [vp, vp, ci, ci, vp, ci, C.POINTER(StepScalars), ci, cf, cf, cf, C.c_uint64,
                                   C.c_int64, vp, vp, vp, vp, vp]
+    lib.mlcg_nonfinite.argtypes = [vp, vp]
     lib.mlcg_num_edge_tiles.argtypes = [vp]
     lib.mlcg_num_edges.argtypes = [vp]
     lib.mlcg_num_edges.restype = C.c_int64

@@ -165,6 +165,7 @@ class MLConformerGenerator:
         else:
             z_known, fixed_mask = prepare_fragment(n_samples, fixed_fragment[0], fixed_fragment[1], max_n_nodes, min_n_nodes)
             x, h = gm.inpaint(node_mask, edge_mask, ctx, z_known, fixed_mask, resample_steps, blend_power)
+        self.engine.check_finite("edm_samples")
         return x, h, node_mask
 
     @torch.no_grad()

@@ -87,6 +87,7 @@ struct mlcg_handle {
   DevBuf s_ld, s_la, s_rowd, s_rowa, s_x64, s_y_op, s_x, s_emb, s_add, s_raw, s_y_f32;
   // mlcg_generate device buffers
   DevBuf g_ctx, g_z, g_x, g_cls, g_el, g_dist, g_adj, g_bonds, g_ids;
+  DevBuf nf_flag;  // set by k_decode when a generated coordinate is not finite (mlcg_nonfinite)
   std::vector<int64_t> ids_stage;
   // test gemm
   DevBuf tg_a, tg_w, tg_b, tg_c;
@@ -212,6 +213,16 @@ static bool edge_dist_fp32(int mode) {
     v = (e == nullptr) ? -1 : (atoi(e) != 0);
   }
   return v < 0 ? (mode == PREC_FP16) : (v != 0);
+}
+// AdjMatSeer GEMMs: error-compensated 3xTF32 (default) or plain tf32 (MLCG_SEER_3XTF32=0: a third of the GEMM time, logits
+// to ~1e-4 instead of ~1e-6; the bond argmax of a random-init GCN then flips on ties below that error).
+static bool seer_split3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLCG_SEER_3XTF32");
+    v = (e == nullptr) ? 1 : (atoi(e) != 0);
+  }
+  return v != 0;
 }
 // CTA-pair mode (default) needs an even grid; MLCG_EDGE_PAIR=0 selects the single-CTA kernel.
 static bool edge_pair_mode() {
@@ -370,7 +381,7 @@ extern "C" void mlcg_destroy(mlcg_handle* h) {
                     &h->h_res, &h->pq, &h->h_op, &h->agg_op, &h->t_op, &h->agg_f32, &h->t_f32, &h->a1, &h->m2, &h->t_dev,
                     &h->eps_dev, &h->s_ld, &h->s_la, &h->s_rowd, &h->s_rowa, &h->s_x64, &h->s_y_op, &h->s_x, &h->s_emb,
                     &h->s_add, &h->s_raw, &h->s_y_f32, &h->g_ctx, &h->g_z, &h->g_x, &h->g_cls, &h->g_el, &h->g_dist,
-                    &h->g_adj, &h->g_bonds, &h->g_ids, &h->tg_a, &h->tg_w, &h->tg_b, &h->tg_c})
+                    &h->g_adj, &h->g_bonds, &h->g_ids, &h->nf_flag, &h->tg_a, &h->tg_w, &h->tg_b, &h->tg_c})
     b->release();
   delete h;
 }
@@ -527,6 +538,7 @@ extern "C" int mlcg_load_seer(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
   auto& m = h->seer_w;
   const char* names[7] = {"gcn1_dm", "gcn2_dm", "gcn3_dm", "gcn1", "gcn2", "gcn3", "gcn4"};
   const int seer_mode = PREC_TF32;  // the GCN always runs kind::tf32 in tensor-core modes (0.2 % of the FLOPs)
+  const int ksplit = seer_split3() ? 3 : 1;  // error-compensated 3xTF32 (default): logits to fp32 accuracy
   auto prep = [&](SeerLayer& S, const std::string& key, int nn, int kk) -> int {
     int r;
     if ((r = need(h, m, key + ".weight", nn, kk, &S.w))) return r;
@@ -537,10 +549,11 @@ extern "C" int mlcg_load_seer(mlcg_handle* h, const mlcg_weight_desc* w, int n) 
     if ((r = pad_vec(h, S.b_pad, S.b.d, 1, nn, npad))) return r;
     if (h->precision == PREC_FP32_SIMT) return MLCG_OK;
     const int kc = (kk + epc(seer_mode) - 1) / epc(seer_mode);
-    CK(S.w_op.ensure((size_t)(npad / 256) * kc * 256 * CHUNK_BYTES));
+    CK(S.w_op.ensure((size_t)(npad / 256) * ksplit * kc * 256 * CHUNK_BYTES));
     PackArgs a{};
-    a.src = S.w.d; a.ld = kk; a.n_real = nn; a.bn = 256; a.n_kc = kc; a.seg_len = kc * epc(seer_mode);
+    a.src = S.w.d; a.ld = kk; a.n_real = nn; a.bn = 256; a.n_kc = ksplit * kc; a.seg_len = kc * epc(seer_mode);
     a.kreal0 = kk; a.kofs0 = 0; a.bias = nullptr; a.bias_k = -1; a.dst = S.w_op.as<uint8_t>();
+    a.split3 = (ksplit == 3);
     CK(launch_pack(seer_mode, a, npad / 256, 0));
     h->launches++;
     return MLCG_OK;
@@ -698,6 +711,7 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   CK(h->h_res.ensure(mpad * HP * sizeof(float)));
   CK(h->pq.ensure(mpad * 2 * HP * sizeof(float)));
   CK(h->t_dev.ensure(B * sizeof(float)));
+  CK(h->nf_flag.ensure(sizeof(int)));
   CK(h->eps_dev.ensure((size_t)B * N * ZC * sizeof(float)));
   if (h->precision == PREC_FP32_SIMT) {
     CK(h->agg_f32.ensure(mpad * HP * sizeof(float)));
@@ -730,6 +744,16 @@ extern "C" int mlcg_set_batch(mlcg_handle* h, const int32_t* n_nodes, int B, int
   return MLCG_OK;
 }
 
+/* 1 if any decode since the last call produced a non-finite coordinate (the trajectory diverged, or -- fp16 mode -- left the
+ * fp16 range), else 0; clears the flag.  Synchronises `stream`. */
+extern "C" int mlcg_nonfinite(mlcg_handle* h, void* stream) {
+  if (!h || !h->nf_flag.p) return 0;
+  int v = 0;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return 0;
+  if (cudaMemcpy(&v, h->nf_flag.p, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  if (v) cudaMemset(h->nf_flag.p, 0, sizeof(int));
+  return v != 0;
+}
 extern "C" int mlcg_num_edge_tiles(mlcg_handle* h) { return h ? h->n_etiles : -1; }
 extern "C" int64_t mlcg_num_edges(mlcg_handle* h) { return h ? h->n_edges : -1; }
 extern "C" int64_t mlcg_kernel_launches(mlcg_handle* h) { return h ? h->launches : -1; }
@@ -1005,7 +1029,7 @@ extern "C" int mlcg_decode(mlcg_handle* h, const float* z0, const float* eps0, f
   STEP_PROLOGUE("decode");
   if (!z0 || !eps0 || !noise || !x || !atom_class) FAIL(MLCG_E_ARG, "decode: null pointer");
   k_decode<<<warp_grid(h->B), 128, 0, st>>>(z0, eps0, h->d_n_nodes.as<int>(), h->B, h->N, sigma_0, alpha_0, sigma_x,
-                                            to_src(h, noise), x, atom_class);
+                                            to_src(h, noise), x, atom_class, h->nf_flag.as<int>());
   KCHECK();
   return MLCG_OK;
 }
@@ -1105,6 +1129,7 @@ static int seer_chunk(mlcg_handle* h, const int32_t* elements, const float* dist
   const bool simt = (h->precision == PREC_FP32_SIMT);
   const int mode = PREC_TF32;
   const int kcH = SEER_H / epc(mode), kcE = SEER_E / epc(mode);
+  const int split3 = (!simt && seer_split3()) ? 1 : 0, ks = split3 ? 3 : 1;
   auto& m = h->seer_w;
   CK(h->s_ld.ensure((size_t)B * SEER_D * SEER_D * 4));
   CK(h->s_la.ensure((size_t)B * SEER_D * SEER_D * 4));
@@ -1116,7 +1141,7 @@ static int seer_chunk(mlcg_handle* h, const int32_t* elements, const float* dist
   CK(h->s_add.ensure(rpad * SEER_E * 4));
   CK(h->s_raw.ensure(rpad * 224 * 4));
   if (simt) CK(h->s_y_f32.ensure(rpad * SEER_H * 4));
-  else CK(h->s_y_op.ensure((size_t)mt * kcH * A_CHUNK_BYTES));
+  else CK(h->s_y_op.ensure((size_t)mt * ks * kcH * A_CHUNK_BYTES));
   k_lnorm<<<B, 64, 0, st>>>(dist, h->s_ld.as<float>(), h->s_rowd.as<float>());
   KCHECK();
   k_lnorm<<<B, 64, 0, st>>>(adj, h->s_la.as<float>(), h->s_rowa.as<float>());
@@ -1131,10 +1156,10 @@ static int seer_chunk(mlcg_handle* h, const int32_t* elements, const float* dist
       return simt_gemm(h, h->s_y_f32.as<float>(), C, S.w.d, S.k, S.b.d, X, SEER_H, R, SEER_H, S.k, SG_BIAS | SG_RELU, lrow, st);
     }
     const int kc = (C == SEER_E) ? kcE : kcH;
-    k_lmul<PREC_TF32><<<g, 128, 0, st>>>(L, xin, C, nullptr, h->s_y_op.as<uint8_t>(), kc);
+    k_lmul<PREC_TF32><<<g, 128, 0, st>>>(L, xin, C, nullptr, h->s_y_op.as<uint8_t>(), kc, split3);
     KCHECK();
     GemmArgs a{};
-    a.a0 = h->s_y_op.as<uint8_t>(); a.a0_chunks = kc; a.a0_per_tile = kc; a.n_kc = kc;
+    a.a0 = h->s_y_op.as<uint8_t>(); a.a0_chunks = ks * kc; a.a0_per_tile = ks * kc; a.n_kc = ks * kc;
     a.w = S.w_op.as<uint8_t>(); a.bias = S.b_pad.as<float>(); a.m_rows = R;
     a.out_f32 = X; a.ldo = SEER_H; a.n_valid = SEER_H; a.rowscale = lrow; a.relu = 1;
     CK((launch_gemm<PREC_TF32, 256, EPI_F32>(a, mt, SEER_H / 256, st)));
@@ -1167,10 +1192,11 @@ static int seer_chunk(mlcg_handle* h, const int32_t* elements, const float* dist
       return rc;
   } else {
     const long long pieces = (long long)R * kcH * 8;
-    k_rowmajor_to_op<PREC_TF32><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(X, SEER_H, R, SEER_H, h->s_y_op.as<uint8_t>(), kcH);
+    k_rowmajor_to_op<PREC_TF32><<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(X, SEER_H, R, SEER_H, h->s_y_op.as<uint8_t>(), kcH,
+                                                                                  split3);
     KCHECK();
     GemmArgs a{};
-    a.a0 = h->s_y_op.as<uint8_t>(); a.a0_chunks = kcH; a.a0_per_tile = kcH; a.n_kc = kcH;
+    a.a0 = h->s_y_op.as<uint8_t>(); a.a0_chunks = ks * kcH; a.a0_per_tile = ks * kcH; a.n_kc = ks * kcH;
     a.w = h->seer_resize.w_op.as<uint8_t>(); a.bias = h->seer_resize.b_pad.as<float>(); a.m_rows = R;
     a.out_f32 = raw; a.ldo = 224; a.n_valid = SEER_D * SEER_NB; a.rowscale = nullptr; a.relu = 0;
     CK((launch_gemm<PREC_TF32, 256, EPI_F32>(a, mt, 1, st)));

@@ -229,7 +229,7 @@ __global__ void k_forward_diffuse(float* __restrict__ z, const float* __restrict
 // atom class = argmax over z0[:, 3:10] (7 channels), padded atoms -> -1.
 __global__ void k_decode(const float* __restrict__ z0, const float* __restrict__ eps_net, const int* __restrict__ n_nodes,
                          int B, int N, float sigma0, float alpha0, float sigma_x, NoiseSrc ns, float* __restrict__ x_out,
-                         int* __restrict__ cls_out) {
+                         int* __restrict__ cls_out, int* __restrict__ nonfinite) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const int n = n_nodes[b];
@@ -248,6 +248,8 @@ __global__ void k_decode(const float* __restrict__ z0, const float* __restrict__
         for (int c = 0; c < 3; ++c) {
           const float mu = __fmul_rn(inv_alpha, __fsub_rn(z0[o + c], __fmul_rn(sigma0, eps_net[o + c])));
           xo[c] = __fadd_rn(mu, __fmul_rn(sigma_x, eps[s][c]));
+          // a diverged trajectory (or, in fp16 mode, one that left the fp16 range) must not pass silently
+          if (nonfinite != nullptr && !isfinite(xo[c])) atomicOr(nonfinite, 1);
         }
         float best = z0[o + 3] * 9.0f;
         cls = 0;
@@ -385,6 +387,9 @@ struct PackArgs {
   const float* bias; int bias_k;
   uint8_t* dst;
   float scale;  // multiplies every packed value (0.5 folds SiLU's half-argument into the weights; 0 is treated as 1)
+  int split3;   // tf32 only: error-compensated split.  The K axis is tripled, W' = [W_hi | W_hi | W_lo] with W_hi = tf32(W),
+                // W_lo = tf32(W - W_hi), to be multiplied with activations laid out as A' = [A_hi | A_lo | A_hi]:
+                // A'.W'^T = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, i.e. the product to ~2^-21 instead of 2^-11 ("3xTF32")
 };
 template <int kMode>
 __global__ void k_pack_weight(const PackArgs a) {
@@ -399,14 +404,16 @@ __global__ void k_pack_weight(const PackArgs a) {
     for (int e = 0; e < EPP; ++e) {
       const int k = kc * EPC + piece * EPP + e;
       const int seg = k / a.seg_len, kk = k - seg * a.seg_len;
-      const int kreal = seg == 0 ? a.kreal0 : a.kreal1;
-      const int kofs = seg == 0 ? a.kofs0 : a.kofs1;
+      const int kreal = (seg == 0 || a.split3) ? a.kreal0 : a.kreal1;
+      const int kofs = (seg == 0 || a.split3) ? a.kofs0 : a.kofs1;
       float x = 0.f;
       if (n < a.n_real) {
-        if (seg < 2 && kk < kreal) x = a.src[(size_t)(a.n_src_off + n) * a.ld + kofs + kk];
+        if ((seg < 2 || (a.split3 && seg < 3)) && kk < kreal) x = a.src[(size_t)(a.n_src_off + n) * a.ld + kofs + kk];
         if (a.bias != nullptr && k == a.bias_k) x = a.bias[a.n_src_off + n];
       }
-      v[e] = x * (a.scale != 0.f ? a.scale : 1.0f);
+      x *= (a.scale != 0.f ? a.scale : 1.0f);
+      if (a.split3 && seg == 2) x -= __uint_as_float(f32_to_tf32(x));  // low part; rounded to tf32 below
+      v[e] = x;
     }
     uint4 w;
     if constexpr (is16(kMode)) {
@@ -427,9 +434,10 @@ __global__ void k_pad_vector(const float* __restrict__ src, int stride, int n_re
 }
 
 // fp32 row-major [rows][ld] -> operand format (used by the AdjMatSeer L-multiply output and tests)
+// split3 (tf32 only): the destination has 3 * n_chunks chunks per tile laid out [A_hi | A_lo | A_hi] (see PackArgs::split3)
 template <int kMode>
 __global__ void k_rowmajor_to_op(const float* __restrict__ src, int ld, int rows, int k_real, uint8_t* __restrict__ dst,
-                                 int n_chunks) {
+                                 int n_chunks, int split3 = 0) {
   constexpr int EPP = epp(kMode), EPC = epc(kMode);
   const int pieces_per_row = n_chunks * 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -439,7 +447,16 @@ __global__ void k_rowmajor_to_op(const float* __restrict__ src, int ld, int rows
   float v[8];
 #pragma unroll
   for (int e = 0; e < EPP; ++e) v[e] = (k0 + e < k_real) ? src[(size_t)row * ld + k0 + e] : 0.f;
-  op_store<kMode, EPP>(dst, n_chunks, row, k0, v);
+  if (!split3) {
+    op_store<kMode, EPP>(dst, n_chunks, row, k0, v);
+  } else {
+    float lo[8];
+#pragma unroll
+    for (int e = 0; e < EPP; ++e) lo[e] = v[e] - __uint_as_float(f32_to_tf32(v[e]));
+    op_store<kMode, EPP>(dst, 3 * n_chunks, row, k0, v);
+    op_store<kMode, EPP>(dst, 3 * n_chunks, row, k0 + n_chunks * EPC, lo);
+    op_store<kMode, EPP>(dst, 3 * n_chunks, row, k0 + 2 * n_chunks * EPC, v);
+  }
 }
 
 // =================================================================================================================
@@ -638,7 +655,7 @@ __global__ void k_seer_embed(const int* __restrict__ elements, const float* __re
 // grid (B, C/128), 128 threads: thread = one column, 42 accumulators.
 template <int kMode>
 __global__ void __launch_bounds__(128) k_lmul(const float* __restrict__ l, const float* __restrict__ x, int C, float* __restrict__ y_f32,
-                                               uint8_t* __restrict__ y_op, int op_chunks) {
+                                               uint8_t* __restrict__ y_op, int op_chunks, int split3 = 0) {
   const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
   __shared__ float ls[SEER_D * SEER_D];
   for (int idx = threadIdx.x; idx < SEER_D * SEER_D; idx += 128) ls[idx] = l[(size_t)b * SEER_D * SEER_D + idx];
@@ -655,8 +672,17 @@ __global__ void __launch_bounds__(128) k_lmul(const float* __restrict__ l, const
 #pragma unroll
   for (int i = 0; i < SEER_D; ++i) {
     const int row = b * SEER_D + i;
-    if constexpr (kMode == PREC_FP32_SIMT) y_f32[(size_t)row * C + c] = acc[i];
-    else op_store1<kMode>(y_op, op_chunks, row, c, acc[i]);
+    if constexpr (kMode == PREC_FP32_SIMT) {
+      y_f32[(size_t)row * C + c] = acc[i];
+    } else if (!split3) {
+      op_store1<kMode>(y_op, op_chunks, row, c, acc[i]);
+    } else {  // [A_hi | A_lo | A_hi], op_chunks = chunks of ONE part
+      const int kp = op_chunks * epc(kMode);
+      const float lo = acc[i] - __uint_as_float(f32_to_tf32(acc[i]));
+      op_store1<kMode>(y_op, 3 * op_chunks, row, c, acc[i]);
+      op_store1<kMode>(y_op, 3 * op_chunks, row, c + kp, lo);
+      op_store1<kMode>(y_op, 3 * op_chunks, row, c + 2 * kp, acc[i]);
+    }
   }
 }
 

@@ -250,6 +250,17 @@ class Engine:
         self._keep = [x_gen, cls_gen, ffx, ffh, shift, rot]
         return zk, fm
 
+    def check_finite(self, what: str = "sample") -> bool:
+        """True if every coordinate decoded since the last check was finite; otherwise warns and returns False.
+        Synchronises the current stream."""
+        if int(self.lib.mlcg_nonfinite(self.h, self._stream())):
+            import warnings
+            warnings.warn("%s: non-finite coordinates were generated -- the trajectory diverged%s" % (
+                what, " or left the fp16 range (pairwise distances > ~1.6e4); precision='bf16' / 'tf32' have fp32's exponent "
+                "range" if self.precision == "fp16" else ""), RuntimeWarning, stacklevel=2)
+            return False
+        return True
+
     def generate_host(self, n_nodes: np.ndarray, max_n_nodes: int, ctx: np.ndarray, T: int = 100,
                       resample_steps: int = 0, seed: int = 0, sample_offset: int = 0, out=None, sample_ids=None,
                       device_out: bool = False):
@@ -278,6 +289,7 @@ class Engine:
                                     None if ids is None else ids.ctypes.data_as(C.c_void_p), _ptr(out[0]),
                                     _ptr(out[1]), _ptr(out[2]), self._stream())
         self._check(rc, "generate")
+        self.check_finite("generate")
         self.B, self.N = B, N
         self.n_nodes = torch.from_numpy(nn.copy())
         return out
