@@ -27,7 +27,7 @@ def main():
     ap.add_argument("n_samples", nargs="?", type=int, default=64)
     ap.add_argument("--edm", default=None)
     ap.add_argument("--seer", default=None)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "tf32", "fp32"])
     args = ap.parse_args()
 
     _, xyz = read_mol_heavy_atoms(args.reference)
