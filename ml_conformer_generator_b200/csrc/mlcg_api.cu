@@ -1249,6 +1249,7 @@ extern "C" int mlcg_generate(mlcg_handle* h, const int32_t* n_nodes_host, int B,
   if (!h) return MLCG_E_ARG;
   if (!h->egnn_loaded || !h->seer_loaded) FAIL(MLCG_E_STATE, "generate: load both weight sets first");
   if (!n_nodes_host || !ctx_host || !steps || !x_host || !atom_class_host || !bonds_host) FAIL(MLCG_E_ARG, "generate: null pointer");
+  CK(cudaSetDevice(h->device));  // the call may come from any host thread (pipeline.GenerationPipeline's feeder)
   cudaStream_t st = (cudaStream_t)stream;
   if (st == nullptr) {
     // the legacy NULL stream cannot be captured; the call is synchronous and takes host buffers, so run it on a

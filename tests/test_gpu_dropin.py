@@ -142,3 +142,31 @@ def test_generate_then_score_shapes(generators):
         d0 = torch.cdist(xc[b, :k], xc[b, :k])
         d1 = torch.cdist(res["aligned_coords"][b, :k], res["aligned_coords"][b, :k])
         assert float((d0 - d1).abs().max()) < 1e-3 * max(1.0, float(d0.max()))  # a rigid motion (possibly a reflection)
+
+
+def test_generate_stream_overlaps_and_equals_one_batch(state_dicts):
+    """generate_stream (GPU generation of batch k + 1 overlapped with CPU post-processing of batch k, feeder thread + worker
+    pool) returns, in order, exactly the molecules one big generate_host call gives for the same seed (the RNG is keyed by
+    the global sample index)."""
+    import numpy as np
+    from ml_conformer_generator_b200 import MLConformerGenerator
+    from ml_conformer_generator_b200.mol_utils import normalise_context
+    gen = MLConformerGenerator(diffusion_steps=3, device=torch.device("cuda:0"), edm_state_dict=state_dicts[0],
+                               adj_mat_seer_state_dict=state_dicts[1])
+    ctx_raw = torch.tensor([53.6424, 108.3042, 151.4399])
+
+    def post(x, cls, bonds, n, index):
+        return index, np.array(x), np.array(cls), np.array(bonds)
+
+    got = [m for batch in gen.generate_stream(ctx_raw, n_atoms=20, n_samples=40, batch_size=16, variance=2, postprocess=post,
+                                              n_workers=3, seed=5) for m in batch]
+    assert [m[0] for m in got] == list(range(40))
+    sizes = torch.randint(18, 23, (40,), generator=torch.Generator().manual_seed(5)).numpy().astype(np.int32)
+    ctx = np.tile(normalise_context(ctx_raw, gen.context_norms).numpy().reshape(1, 3), (40, 1)).astype(np.float32)
+    x, cls, bonds = gen.engine.generate_host(sizes, 22, ctx, 3, 0, seed=5)
+    for i, (_, xi, ci, bi) in enumerate(got):
+        n = int(sizes[i])
+        assert np.array_equal(xi, x[i, :n].numpy()) and np.array_equal(ci, cls[i, :n].numpy()) and np.array_equal(bi, bonds[i].numpy())
+    blocks = [b for batch in gen.generate_stream(ctx_raw, n_atoms=20, n_samples=10, batch_size=4, seed=1) for b in batch]
+    assert len(blocks) == 10 and all(b.endswith("$$$$\n") for b in blocks)
+    gen.engine.close()
