@@ -9,7 +9,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmlcg_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("mlcg_api.cu", "mlcg_tc.cuh", "mlcg_kernels.cuh", "mlcg_shape.cuh", "mlcg_ifm.cuh",
+SOURCES = [os.path.join(_HERE, "csrc", f) for f in ("mlcg_api.cu", "mlcg_tc.cuh", "mlcg_tc3.cuh", "mlcg_kernels.cuh", "mlcg_shape.cuh", "mlcg_ifm.cuh",
                                                      "mlcg_common.cuh")]
 HEADER = os.path.join(_ROOT, "include", "mlcg.h")
 

@@ -10,6 +10,7 @@
 #include "mlcg.h"
 #include "mlcg_kernels.cuh"
 #include "mlcg_tc.cuh"
+#include "mlcg_tc3.cuh"
 #include "mlcg_shape.cuh"
 #include "mlcg_ifm.cuh"
 
@@ -260,9 +261,58 @@ static void edge_tile_owner(int num_sms, int n_tiles, std::vector<int>& owner) {
     }
   }
 }
+// k_tc_edge3 (mlcg_tc3.cuh): resident A operand + two ping-pong 144-column accumulators.  16-bit modes, CTA pairs.
+template <int kMode, bool kEquiv, bool kDistF32, bool kProf = false>
+static cudaError_t launch_edge3(const EdgeArgs& a, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_edge3<kMode, kEquiv, kDistF32, kProf>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Edge3Smem<kMode, kEquiv>::ALLOC);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(EDGE_THREADS);
+  cfg.dynamicSmemBytes = Edge3Smem<kMode, kEquiv>::ALLOC;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_tc_edge3<kMode, kEquiv, kDistF32, kProf>, a);
+}
+// MLCG_EDGE_V3=1 selects k_tc_edge3 in the 16-bit modes, 0 the single-accumulator kernel k_tc_edge
+static bool edge_v3_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLCG_EDGE_V3");
+    v = (e == nullptr) ? 0 : (atoi(e) != 0);  // work in progress: opt-in until it beats k_tc_edge on every workload
+  }
+  return v != 0;
+}
 static cudaError_t launch_edge_mode(int mode, bool equiv, const EdgeArgs& a, int grid, cudaStream_t st, bool prof = false) {
   const bool pair = edge_pair_mode() && grid >= 2;
   if (pair) grid &= ~1;
+  if (prof && pair && is16(mode) && edge_v3_mode() && a.n_kc == E3_NKC) {
+    // instrumented instantiations of the default variant of each mode
+    if (edge_dist_fp32(mode) != (mode == PREC_FP16)) return cudaErrorNotSupported;
+    if (mode == PREC_FP16)
+      return equiv ? launch_edge3<PREC_FP16, true, true, true>(a, grid, st) : launch_edge3<PREC_FP16, false, true, true>(a, grid, st);
+    return equiv ? launch_edge3<PREC_BF16, true, false, true>(a, grid, st) : launch_edge3<PREC_BF16, false, false, true>(a, grid, st);
+  }
+  if (!prof && pair && is16(mode) && edge_v3_mode() && a.n_kc == E3_NKC) {
+    const bool df = edge_dist_fp32(mode);
+    if (mode == PREC_FP16) {
+      if (df) return equiv ? launch_edge3<PREC_FP16, true, true>(a, grid, st) : launch_edge3<PREC_FP16, false, true>(a, grid, st);
+      return equiv ? launch_edge3<PREC_FP16, true, false>(a, grid, st) : launch_edge3<PREC_FP16, false, false>(a, grid, st);
+    }
+    if (df) return equiv ? launch_edge3<PREC_BF16, true, true>(a, grid, st) : launch_edge3<PREC_BF16, false, true>(a, grid, st);
+    return equiv ? launch_edge3<PREC_BF16, true, false>(a, grid, st) : launch_edge3<PREC_BF16, false, false>(a, grid, st);
+  }
   if (prof) {
     // instrumented instantiations exist for the default variant of each mode only (CTA pairs, default distance terms)
     if (!pair || edge_dist_fp32(mode) != (mode == PREC_FP16)) return cudaErrorNotSupported;
@@ -1379,6 +1429,7 @@ extern "C" int mlcg_edge_phase_profile(mlcg_handle* h, int layer, double* out, v
   const int grid_e = edge_grid(h);
   DevBuf buf;
   CK(buf.ensure((size_t)grid_e * 16 * sizeof(long long)));
+  CK(cudaMemsetAsync(buf.p, 0, (size_t)grid_e * 16 * sizeof(long long), st));
   EdgeArgs ea = edge_args(h, L, h->xa.as<float>(), h->xb.as<float>());
   ea.prof = buf.as<long long>();
   CK(launch_edge_mode(h->precision, L.equiv, ea, grid_e, st, true));

@@ -1,6 +1,7 @@
 """Thin Python host over the C ABI: owns one `mlcg_handle`, keeps torch tensors alive across asynchronous calls, and
 converts the reference's tensor conventions (float masks, (B,N,3) context) into the library's (atom counts, (B,3))."""
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -312,6 +313,13 @@ class Engine:
         self._check(self.lib.mlcg_edge_phase_profile(self.h, layer, out, self._stream()), "edge_phase_profile")
         names = ["rowinfo_pq_wait", "a_gen", "mma_tail", "pass1", "pass2", "a_ring_backpressure", "tiles",
                  "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout", "a_handoff"]
+        if self.precision in ("fp16", "bf16") and os.environ.get("MLCG_EDGE_V3", "0") != "0" and \
+                os.environ.get("MLCG_EDGE_PAIR", "1") != "0":
+            # k_tc_edge3 (mlcg_tc3.cuh): per tile, thread 0 of the compute warps; the last two are the MMA issuer's waits
+            # (leader CTAs only, i.e. half the per-tile value)
+            names = ["wait_third0", "pass1_third0", "wait_third1", "pass1_third1", "barrier_pq_wait", "agen_early", "tiles",
+                     "wait_third2", "pass1_third2", "gate_selector", "agen_rest", "wait_segsum", "readout", "end_barrier",
+                     "issuer_wait_a", "issuer_wait_w"]
         return {n: float(out[i]) for i, n in enumerate(names)}
 
     def gemm_phase_profile(self, which: int) -> dict:
