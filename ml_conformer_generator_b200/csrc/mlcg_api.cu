@@ -285,12 +285,12 @@ static cudaError_t launch_edge3(const EdgeArgs& a, int grid, cudaStream_t st) {
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_tc_edge3<kMode, kEquiv, kDistF32, kProf>, a);
 }
-// MLCG_EDGE_V3=1 selects k_tc_edge3 in the 16-bit modes, 0 the single-accumulator kernel k_tc_edge
+// MLCG_EDGE_V3=0 selects the single-accumulator kernel k_tc_edge in the 16-bit modes (A/B measurements); default: k_tc_edge3
 static bool edge_v3_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MLCG_EDGE_V3");
-    v = (e == nullptr) ? 0 : (atoi(e) != 0);  // work in progress: opt-in until it beats k_tc_edge on every workload
+    v = (e == nullptr) ? 1 : (atoi(e) != 0);
   }
   return v != 0;
 }

@@ -54,7 +54,9 @@ struct Edge3Smem {
   static constexpr int RID_OFF = TRS_OFF + 2 * TILE_M * 3 * 4;
   static constexpr int RIG_OFF = RID_OFF + 2 * TILE_M * 8;
   static constexpr int WV_OFF = RIG_OFF + 2 * TILE_M * 4;
-  static constexpr int BAR_OFF = WV_OFF + HP * 4;
+  static constexpr int WCD_OFF = WV_OFF + HP * 4;   // first-layer columns of the two distance features: wc[448] | wd[448] fp32, or
+                                                   // the packed 16-bit table wcd_h[448]
+  static constexpr int BAR_OFF = WCD_OFF + 2 * HP * 4;
   static constexpr int PROF_OFF = BAR_OFF + 1024;  // barriers: 3 per W slot + 2 per K chunk + 10, then the TMEM slot   // 16 x int64 phase counters (diagnostics)
   static constexpr int TOTAL = PROF_OFF + 128;
   static constexpr int ALLOC = TOTAL + 1024;
@@ -93,6 +95,21 @@ __device__ __forceinline__ void umma_commit_pair_e(uint32_t bar, uint16_t mask) 
       "h"(mask)
       : "memory");
 }
+// one elected lane of a convergent warp: expect_tx + 1-D bulk copy global -> shared
+__device__ __forceinline__ void bulk_g2s_expect_e(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+      "@pe cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_e(uint32_t cluster_addr) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+      "@pe mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(cluster_addr)
+      : "memory");
+}
 // mbarrier wait whose spin loop (with the timeout bookkeeping of mbar_wait) is out of line: the fast path is one try_wait
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
@@ -106,6 +123,19 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
       : "memory");
   if (!done) mbar_wait_slow(bar, parity);
 }
+// the same for a convergent warp: the branch to the slow path is taken by all lanes or none (warp vote), which keeps the
+// control flow -- and with it the loop variables of the caller -- uniform
+__device__ __forceinline__ void mbar_wait_lean_w(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (!__all_sync(0xffffffffu, done != 0)) mbar_wait_slow(bar, parity);
+}
 // non-blocking test of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -117,6 +147,87 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "r"(bar), "r"(parity)
       : "memory");
   return done != 0;
+}
+
+// mbarrier slots of k_tc_edge3 (8 bytes each, from BAR_OFF)
+template <int NW>
+struct E3Bar {
+  static constexpr int W_FULL = 0, W_EMPTY = NW, W_PEER = 2 * NW, A_FULL = 3 * NW, A_FREE = 3 * NW + E3_NKC, PQ_FULL = 3 * NW + 2 * E3_NKC,
+                       PQ_EMPTY = PQ_FULL + 1, D_FULL = PQ_FULL + 2, D_FREE = PQ_FULL + 4, E_FULL = PQ_FULL + 6, E_DONE = PQ_FULL + 7,
+                       TMEM_SLOT = PQ_FULL + 10;
+};
+
+// The tcgen05.mma issuer of k_tc_edge3: warp 1 of the leader CTA, all 32 lanes convergent, the tcgen05 instructions issued
+// by one elected lane.  A straight-line tcgen05.mma costs ~45 issue cycles and an N = 144 MMA executes in 72
+// (tools/probe_mma_rate2.cu), so the bookkeeping per MMA has to stay within a handful of instructions.  That only works if the
+// compiler keeps descriptors, TMEM addresses and barrier addresses in UNIFORM registers: hence a separate (non-inlined)
+// function whose every input is provably warp-uniform -- the tile count re-broadcast with a shuffle, the shared-memory base
+// re-derived from the symbol, no calls inside the loops (a call spills the uniform registers), warp votes on every barrier test
+// -- and whose register allocation is independent of the compute warps' code.  The K-chunk and k-step loops are unrolled
+// (constant TMEM / descriptor offsets); a W slot is ONE barrier (the peer's relay arrives on the leader's w_full).
+template <int kMode, bool kSeg, class S>
+__device__ __forceinline__ void edge3_issuer(int n_iter_in) {
+  constexpr int NW = S::E3_NW;
+  using B = E3Bar<NW>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = base + S::BAR_OFF;
+  const int n_iter = __shfl_sync(0xffffffffu, n_iter_in, 0);
+  constexpr uint32_t tmem_base = 0u;  // checked by the kernel
+  constexpr uint32_t idesc = umma_idesc(umma_fmt(kMode), 2 * TILE_M, E3_NT);
+  // (the segment-sum MMAs of the GCL variant are issued by warp 0, see edge3_issue_seg: they are independent of the thirds
+  // -- other accumulator, released by d_free -- and this warp is the bottleneck of the tensor pipe)
+  const uint64_t w_desc0 = umma_desc_sw128(base + S::W_OFF);
+  uint32_t ws = 0, wph = 0;  // current W ring slot and its phase parity
+  for (int it = 0; it < n_iter; ++it) {
+    auto third = [&](auto n3c) {
+      constexpr int n3 = decltype(n3c)::value;
+      const int G = 3 * it + n3, acc = G & 1, u = G >> 1;
+      if (G >= 2) mbar_wait_lean_w(bar0 + 8u * (B::D_FREE + acc), (uint32_t)((u - 1) & 1));
+      tc_fence_after();
+      const uint32_t dcol = tmem_base + E3_DCOL0 + acc * E3_NT;
+#pragma unroll
+      for (int kc = 0; kc < E3_NKC; ++kc) {
+        if (n3 == 0) {
+          mbar_wait_lean_w(bar0 + 8u * (B::A_FULL + kc), (uint32_t)(it & 1));
+        }
+        mbar_wait_lean_w(bar0 + 8u * (B::W_FULL + ws), wph);  // both halves of the block: own bulk copy + the peer's relay
+        tc_fence_after();
+        const uint64_t bdesc = w_desc0 + (uint64_t)(ws * (E3_WSLOT >> 4));
+        // the last chunk's fourth k-step (K 432..447) is all padding: A and W2 are zero there
+#pragma unroll
+        for (int ks = 0; ks < ((kc == E3_NKC - 1) ? 3 : 4); ++ks)
+          umma_ts_pair_e(dcol, tmem_base + kc * 32 + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+        umma_commit_pair_e(bar0 + 8u * (B::W_EMPTY + ws), 3);
+        if (n3 == 2) umma_commit_pair_e(bar0 + 8u * (B::A_FREE + kc), 3);  // the next tile's A chunk kc may be written
+        if (++ws == NW) { ws = 0; wph ^= 1u; }
+      }
+      umma_commit_pair_e(bar0 + 8u * (B::D_FULL + acc), 3);
+    };
+    third(std::integral_constant<int, 0>{});
+    third(std::integral_constant<int, 1>{});
+    third(std::integral_constant<int, 2>{});
+  }
+}
+
+// Segment sum of tile j on the tensor core (GCL): D2[128 channels x 32 (16 groups of CTA 0 | 16 of CTA 1)] per 128-channel
+// block = E^T . S'^T with E the staged messages (MN-major A operand) and S' the gate-weighted selector, into the accumulator
+// that tile j's last third used.  Issued by warp 0 of the leader CTA (convergent, one elected lane).
+template <int kMode, class S>
+__device__ __forceinline__ void edge3_issue_seg(uint32_t base, int j) {
+  using B = E3Bar<S::E3_NW>;
+  constexpr uint32_t idesc2 = umma_idesc(umma_fmt(kMode), 2 * TILE_M, 32) | (1u << 15);  // A is MN-major
+  const uint64_t seg_a0 = umma_desc_mn_sw128(base + S::STG_OFF, A_CHUNK_BYTES);
+  const uint64_t seg_b0 = umma_desc_sw128(base + S::SEL_OFF);
+  const uint32_t dcol = E3_DCOL0 + ((3 * j + 2) & 1) * E3_NT;
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb) {
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      umma_ss_pair_e(dcol + cb * 32, seg_a0 + (uint64_t)((cb * 2 * A_CHUNK_BYTES + ks * 2048) >> 4),
+                     seg_b0 + (uint64_t)(((ks >> 2) * 2048) >> 4) + 2 * (ks & 3), idesc2, ks != 0);
+  }
+  umma_commit_pair_e(base + S::BAR_OFF + 8u * B::E_DONE, 3);
 }
 
 // kProf: phase cycle counters (mlcg_edge_phase_profile): thread ct == 0 of every CTA accumulates [0] wait third 0, [1] pass 1
@@ -156,9 +267,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
   const uint32_t e_done = pq_full + 56u;                                   // segment-sum MMAs complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + S::BAR_OFF + 8 * (3 * E3_NW + 2 * E3_NKC + 10));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a broadcast shuffle: tells the compiler that it is warp-uniform, so the role branches below are
+  // uniform branches and the service warps' loop variables / descriptors can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // tile range of the pair: identical to k_tc_edge<.., kPair = true> (edge_tile_owner on the host mirrors it)
-  const uint32_t crank = cluster_ctarank();
+  const uint32_t crank = (uint32_t)__shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0);  // (uniform for the compiler, see above)
   int t_begin, t_end, n_iter;
   {
     const int npairs = gridDim.x >> 1, pr = blockIdx.x >> 1;
@@ -202,6 +315,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) wv_s[i] = p.wv[i] * (1.0f / act_scale(kMode));
+  // The distance-feature columns are read once per K chunk by every thread with a warp-uniform index.  From the constant
+  // bank that is an indexed LDC, which measures ~8 issue cycles per warp instruction (tools/probe_alu.cu) -- as much as the
+  // MUFU work of the chunk; from shared memory it is a broadcast LDS.128 (one wavefront).
+  float* wc_s = reinterpret_cast<float*>(gbase + S::WCD_OFF);
+  float* wd_s = wc_s + HP;
+  uint32_t* wcdh_s = reinterpret_cast<uint32_t*>(gbase + S::WCD_OFF);
+  if constexpr (kDistF32) {
+    for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) { wc_s[i] = p.wc[i]; wd_s[i] = p.wd[i]; }
+  } else {
+    for (int i = threadIdx.x; i < HP; i += EDGE_THREADS) wcdh_s[i] = p.wcd_h[i];
+  }
   if (warp == 1) tmem_alloc_pair<512>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
@@ -218,135 +342,76 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
 
   if (warp == 0) {
     // ===================== bulk-copy producer: P/Q rows per tile, W2 blocks per (third, K chunk) =====================
-    if (lane == 0) {
-      int prev_mol = -1;
-      auto load_pq = [&](int j) {
-        const EdgeTile tj = fetch_tile(j);
-        const int node0 = p.node_off[tj.mol];
-        if (j > 0) mbar_wait(pq_empty, (uint32_t)((j - 1) & 1));
-        const bool newmol = (tj.mol != prev_mol);
-        mbar_arrive_expect_tx(pq_full, (uint32_t)((tj.ng + (newmol ? tj.n : 0)) * S::PQ_ROW));
-        const uint8_t* pqb = reinterpret_cast<const uint8_t*>(p.pq);
-        for (int g = 0; g < tj.ng; ++g)
-          bulk_g2s(base + S::P_OFF + g * S::PQ_PITCH, pqb + (size_t)(node0 + tj.i0 + g) * (2 * S::PQ_ROW), S::PQ_ROW, pq_full);
-        if (newmol)
-          for (int j2 = 0; j2 < tj.n; ++j2)
-            bulk_g2s(base + S::Q_OFF + j2 * S::PQ_PITCH, pqb + (size_t)(node0 + j2) * (2 * S::PQ_ROW) + S::PQ_ROW, S::PQ_ROW, pq_full);
-        prev_mol = tj.mol;
-      };
-      if (n_iter > 0) load_pq(0);
-      uint32_t wi = 0;
-      for (int it = 0; it < n_iter; ++it)
-        for (int n3 = 0; n3 < 3; ++n3)
-          for (int kc = 0; kc < E3_NKC; ++kc, ++wi) {
-            // the next tile's P/Q rows: requested once the second third is under way (the A generation of this tile is
-            // complete by then, so pq_empty does not block the weight stream), needed one third later
-            if (n3 == 1 && kc == 5 && it + 1 < n_iter) load_pq(it + 1);
-            const int s = wi % E3_NW;
-            mbar_wait(w_empty(s), ((wi / E3_NW) & 1) ^ 1u);
-            mbar_arrive_expect_tx(w_full(s), E3_WSLOT);
-            const uint8_t* src = p.w2 + (size_t)kc * (HP * CHUNK_BYTES) + (size_t)(E3_NT * n3 + 72 * crank) * CHUNK_BYTES;
-            bulk_g2s(base + S::W_OFF + s * E3_WSLOT, src, E3_WSLOT, w_full(s));
+    // The whole warp runs the loop convergently.  W2 blocks: one elected lane per block (21 per tile; the loop is unrolled so
+    // that the source offsets are constants and the slot / phase are running variables -- at ~290 cycles per block in the
+    // full-rate thirds a scalar loop with index arithmetic cannot keep up).  P/Q rows: lane l issues row l, so the 12 (+ 39
+    // on a molecule change) row copies of a tile cost a few hundred cycles of this warp instead of thousands.
+    int prev_mol = -1;
+    auto load_pq = [&](int j) {
+      const EdgeTile tj = fetch_tile(j);
+      const int node0 = p.node_off[tj.mol];
+      if (j > 0) mbar_wait_lean_w(pq_empty, (uint32_t)((j - 1) & 1));
+      const bool newmol = (tj.mol != prev_mol);
+      if (lane == 0) mbar_arrive_expect_tx(pq_full, (uint32_t)((tj.ng + (newmol ? tj.n : 0)) * S::PQ_ROW));
+      __syncwarp();
+      const uint8_t* pqb = reinterpret_cast<const uint8_t*>(p.pq);
+      if (lane < tj.ng)
+        bulk_g2s(base + S::P_OFF + lane * S::PQ_PITCH, pqb + (size_t)(node0 + tj.i0 + lane) * (2 * S::PQ_ROW), S::PQ_ROW, pq_full);
+      if (newmol)
+        for (int j2 = lane; j2 < tj.n; j2 += 32)
+          bulk_g2s(base + S::Q_OFF + j2 * S::PQ_PITCH, pqb + (size_t)(node0 + j2) * (2 * S::PQ_ROW) + S::PQ_ROW, S::PQ_ROW, pq_full);
+      __syncwarp();
+      prev_mol = tj.mol;
+    };
+    if (n_iter > 0) load_pq(0);
+    uint32_t ws = 0, wph = 1;  // slot and the parity of "empty" to wait for (first pass: slots start empty)
+    const uint8_t* wsrc = p.w2 + (size_t)(72 * crank) * CHUNK_BYTES;
+    for (int it = 0; it < n_iter; ++it) {
+#pragma unroll
+      for (int n3 = 0; n3 < 3; ++n3) {
+#pragma unroll
+        for (int kc = 0; kc < E3_NKC; ++kc) {
+          // the next tile's P/Q rows: requested once the second third is under way (the A generation of this tile is
+          // complete by then, so pq_empty does not block the weight stream), needed one third later
+          if (n3 == 1 && kc == 5 && it + 1 < n_iter) load_pq(it + 1);
+          if constexpr (kSeg) {
+            // the previous tile's segment sum: its messages are staged and its selector is built once the compute warps are
+            // through pass 1 of its last third, i.e. while they generate this tile's A chunks 2..; the weight blocks up to
+            // here cover that stretch
+            if (n3 == 0 && kc == 5 && it > 0 && crank == 0) {
+              mbar_wait_lean_w(e_full, (uint32_t)((it - 1) & 1));
+              tc_fence_after();
+              edge3_issue_seg<kMode, S>(base, it - 1);
+            }
           }
+          mbar_wait_lean_w(w_empty(ws), wph);
+          bulk_g2s_expect_e(base + S::W_OFF + ws * E3_WSLOT, wsrc + (size_t)kc * (HP * CHUNK_BYTES) + (size_t)(E3_NT * n3) * CHUNK_BYTES,
+                            E3_WSLOT, w_full(ws));
+          if (++ws == E3_NW) { ws = 0; wph ^= 1u; }
+        }
+      }
+    }
+    if constexpr (kSeg) {
+      if (crank == 0 && n_iter > 0) {  // the last tile's segment sum
+        mbar_wait_lean_w(e_full, (uint32_t)((n_iter - 1) & 1));
+        tc_fence_after();
+        edge3_issue_seg<kMode, S>(base, n_iter - 1);
+      }
     }
   } else if (warp == 1) {
     if (crank == 1) {
-      if (lane == 0) {
-      // peer CTA: relay "my half of W slot s has landed" to the leader, which issues the joint MMAs
+      // peer CTA: relay "my half of W slot s has landed" to the leader, which issues the joint MMAs (convergent warp, one
+      // elected lane arrives)
       const uint32_t total = (uint32_t)n_iter * 3u * E3_NKC;
+      uint32_t ws = 0, wph = 0;
       for (uint32_t wi = 0; wi < total; ++wi) {
-        const int s = wi % E3_NW;
-        mbar_wait(w_full(s), (wi / E3_NW) & 1);
-        mbar_arrive_cluster(mapa(w_full(s), 0));
-      }
+        mbar_wait_lean_w(w_full(ws), wph);
+        mbar_arrive_cluster_e(mapa(w_full(ws), 0));
+        if (++ws == E3_NW) { ws = 0; wph ^= 1u; }
       }
     } else {
       // ===================== tcgen05.mma issuer (leader CTA) =====================
-      // The whole warp runs this loop convergently (every value is warp-uniform, so descriptors and TMEM addresses live in
-      // uniform registers); the tcgen05 instructions themselves are issued by one elected lane (elect.sync inside the asm).
-      // One thread issues every MMA of the pair.  A straight-line tcgen05.mma costs ~45 issue cycles and an N = 144 MMA
-      // executes in 72 (tools/probe_mma_rate2.cu), so the per-block bookkeeping has to stay within a few dozen instructions:
-      // the K-chunk and k-step loops are fully unrolled (constant TMEM / descriptor offsets), the ring slot and its phase are
-      // running variables, a W slot is ONE barrier (the peer's relay arrives on the leader's w_full), and the timeout
-      // bookkeeping of the mbarrier wait lives out of line.
-      constexpr uint32_t idesc = umma_idesc(umma_fmt(kMode), 2 * TILE_M, E3_NT);
-      constexpr uint32_t idesc2 = umma_idesc(umma_fmt(kMode), 2 * TILE_M, 32) | (1u << 15);  // segment sum: A is MN-major
-      // segment sum of tile j on the tensor core: D2[128 channels x 32 (16 groups of CTA 0 | 16 of CTA 1)] per 128-channel
-      // block, into the accumulator that tile j's last third used
-      const uint64_t seg_a0 = umma_desc_mn_sw128(base + S::STG_OFF, A_CHUNK_BYTES);
-      const uint64_t seg_b0 = umma_desc_sw128(base + S::SEL_OFF);
-      auto issue_seg = [&](int j) {
-        const uint32_t dcol = tmem_base + E3_DCOL0 + ((3 * j + 2) & 1) * E3_NT;
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_ss_pair_e(dcol + cb * 32, seg_a0 + (uint64_t)((cb * 2 * A_CHUNK_BYTES + ks * 2048) >> 4),
-                              seg_b0 + (uint64_t)(((ks >> 2) * 2048) >> 4) + 2 * (ks & 3), idesc2, ks != 0);
-        }
-        umma_commit_pair_e(e_done, 3);
-      };
-      const uint64_t w_desc0 = umma_desc_sw128(base + S::W_OFF);
-      uint32_t ws = 0, wph = 0;  // current W ring slot and its phase parity
-      bool seg_pending = false;
-      long long w_a = 0, w_w = 0;
-      const bool iprof = kProf && p.prof != nullptr;
-      for (int it = 0; it < n_iter; ++it) {
-        auto third = [&](auto n3c) {
-          constexpr int n3 = decltype(n3c)::value;
-          const int G = 3 * it + n3, acc = G & 1, u = G >> 1;
-          if (kSeg && n3 == 1 && seg_pending) {  // not issued during the first third: do it now (blocking)
-            mbar_wait_lean(e_full, (uint32_t)((it - 1) & 1));
-            tc_fence_after();
-            issue_seg(it - 1);
-            seg_pending = false;
-          }
-          {
-            const long long c0 = iprof ? clock64() : 0;
-            if (G >= 2) mbar_wait_lean(d_free(acc), (uint32_t)((u - 1) & 1));
-            if (iprof) w_a += clock64() - c0;
-          }
-          tc_fence_after();
-          const uint32_t dcol = tmem_base + E3_DCOL0 + acc * E3_NT;
-#pragma unroll
-          for (int kc = 0; kc < E3_NKC; ++kc) {
-            if (n3 == 0) {
-              mbar_wait_lean(a_full(kc), (uint32_t)(it & 1));
-              if (kSeg && seg_pending && mbar_test(e_full, (uint32_t)((it - 1) & 1))) {
-                tc_fence_after();
-                issue_seg(it - 1);
-                seg_pending = false;
-              }
-            }
-            const long long c1 = iprof ? clock64() : 0;
-            mbar_wait_lean(w_full(ws), wph);  // both halves of the block: own bulk copy + the peer's relay
-            if (iprof && n3 > 0) w_w += clock64() - c1;
-            tc_fence_after();
-            const uint64_t bdesc = w_desc0 + (uint64_t)(ws * (E3_WSLOT >> 4));
-            // the last chunk's fourth k-step (K 432..447) is all padding: A and W2 are zero there
-#pragma unroll
-            for (int ks = 0; ks < ((kc == E3_NKC - 1) ? 3 : 4); ++ks)
-              umma_ts_pair_e(dcol, tmem_base + kc * 32 + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
-            umma_commit_pair_e(w_empty(ws), 3);
-            if (n3 == 2) umma_commit_pair_e(a_free(kc), 3);  // the next tile's A chunk kc may be written
-            if (++ws == E3_NW) { ws = 0; wph ^= 1u; }
-          }
-          umma_commit_pair_e(d_full(acc), 3);
-        };
-        third(std::integral_constant<int, 0>{});
-        third(std::integral_constant<int, 1>{});
-        third(std::integral_constant<int, 2>{});
-        if (kSeg) seg_pending = true;
-      }
-      if (kSeg && seg_pending) {
-        mbar_wait_lean(e_full, (uint32_t)((n_iter - 1) & 1));
-        tc_fence_after();
-        issue_seg(n_iter - 1);
-      }
-      if (iprof && lane == 0) {
-        p.prof[(size_t)blockIdx.x * 16 + 14] = w_a;
-        p.prof[(size_t)blockIdx.x * 16 + 15] = w_w;
-      }
+      edge3_issuer<kMode, kSeg, S>(n_iter);
     }
   } else {
     // ===================== compute warps: A generation, pass 1 per third, gate / segment-sum readout =====================
@@ -433,30 +498,28 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
         a_pend = -1;
       }
     };
-    // One K chunk of the A operand of tile j: SiLU(P_i + Q_j + d2*wc + d02*wd) -> TMEM columns 32*kc + 8*qq .. +7
-    auto agen_chunk = [&](int j, int kc, const RowIn& ri) {
-      const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform
-      uint32_t w[8];
+    // A generation of tile j, K chunks kc0 .. kc1-1: SiLU(P_i + Q_j + d2*wc + d02*wd) -> TMEM columns 32*kc + 8*qq .. +7.
+    // Software-pipelined over the chunks: the pre-activations of chunk kc+1 (shared-memory / constant-bank loads, packed adds,
+    // fp32 distance terms: FMA-pipe work) are computed in the same straight-line region as the activation of chunk kc (MUFU
+    // work), so that the scheduler interleaves the two.  Without this all four warps of a sub-partition run load -> FMA ->
+    // MUFU -> store in lock step (they synchronise on every tile) and the two pipes take turns idling.
+    auto agen_pre = [&](int kc, const RowIn& ri, uint32_t* h) {
+      const int k0 = kc * EPC + qq * ELEMS;  // warp-uniform.  K columns >= 420 are padding: P, Q, wc, wd are zero there
 #pragma unroll
       for (int e = 0; e < ELEMS; e += 8) {
-        // K columns >= 424 are padding of the 420 (+ bias column) real ones: their weights are zero
-        if (k0 + e >= 424) {
-          w[(e >> 1) + 0] = w[(e >> 1) + 1] = w[(e >> 1) + 2] = w[(e >> 1) + 3] = 0u;
-          continue;
-        }
         const uint4 pw = *reinterpret_cast<const uint4*>(ri.P + (kc * EPC + e) * 2);
         const uint4 qw = *reinterpret_cast<const uint4*>(ri.Q + (kc * EPC + e) * 2);
         const uint32_t pa[4] = {pw.x, pw.y, pw.z, pw.w}, qa[4] = {qw.x, qw.y, qw.z, qw.w};
         [[maybe_unused]] uint32_t wcp[4], wdp[4];
         [[maybe_unused]] float wcv[8], wdv[8];
         if constexpr (kDistF32) {
-          const float4 a0 = *reinterpret_cast<const float4*>(&p.wc[k0 + e]), a1 = *reinterpret_cast<const float4*>(&p.wc[k0 + e + 4]);
-          const float4 b0 = *reinterpret_cast<const float4*>(&p.wd[k0 + e]), b1 = *reinterpret_cast<const float4*>(&p.wd[k0 + e + 4]);
+          const float4 a0 = *reinterpret_cast<const float4*>(wc_s + k0 + e), a1 = *reinterpret_cast<const float4*>(wc_s + k0 + e + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(wd_s + k0 + e), b1 = *reinterpret_cast<const float4*>(wd_s + k0 + e + 4);
           wcv[0] = a0.x; wcv[1] = a0.y; wcv[2] = a0.z; wcv[3] = a0.w; wcv[4] = a1.x; wcv[5] = a1.y; wcv[6] = a1.z; wcv[7] = a1.w;
           wdv[0] = b0.x; wdv[1] = b0.y; wdv[2] = b0.z; wdv[3] = b0.w; wdv[4] = b1.x; wdv[5] = b1.y; wdv[6] = b1.z; wdv[7] = b1.w;
         } else {
-          const uint4 c0 = *reinterpret_cast<const uint4*>(&p.wcd_h[(k0 + e)]);
-          const uint4 c1 = *reinterpret_cast<const uint4*>(&p.wcd_h[(k0 + e) + 4]);
+          const uint4 c0 = *reinterpret_cast<const uint4*>(wcdh_s + (k0 + e));
+          const uint4 c1 = *reinterpret_cast<const uint4*>(wcdh_s + (k0 + e) + 4);
           wcp[0] = c0.x; wcp[1] = c0.y; wcp[2] = c1.x; wcp[3] = c1.y;
           wdp[0] = c0.z; wdp[1] = c0.w; wdp[2] = c1.z; wdp[3] = c1.w;
         }
@@ -471,8 +534,22 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
             h2 = hfma2<kMode>(ri.d2h, wcp[i], h2);
             h2 = hfma2<kMode>(ri.d02h, wdp[i], h2);
           }
-          w[(e >> 1) + i] = hsilu2<kMode>(h2);
+          h[(e >> 1) + i] = h2;
         }
+      }
+    };
+    auto agen_post = [&](int j, int kc, const uint32_t* h, auto skip_pad) {
+      const int k0 = kc * EPC + qq * ELEMS;
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < ELEMS; e += 8) {
+        // last chunk only: K columns >= 424 are all padding, skip their MUFU work (the activation of 0 is 0)
+        if (decltype(skip_pad)::value && k0 + e >= 424) {
+          w[(e >> 1) + 0] = w[(e >> 1) + 1] = w[(e >> 1) + 2] = w[(e >> 1) + 3] = 0u;
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[(e >> 1) + i] = hsilu2<kMode>(h[(e >> 1) + i]);
       }
       // constant-1 column carrying b2 (K index 420 = element 4 of the run that starts at 416): low half of word 2
       if (k0 == BIAS_COL - 4) w[2] = (w[2] & 0xffff0000u) | h_act_one_bits<kMode>();
@@ -482,15 +559,27 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
       tmem_st8(trow + kc * 32 + qq * 8, w);
       a_pend = kc;
     };
+    auto agen_run = [&](int j, int kc0, int kc1, const RowIn& ri) {
+      uint32_t h[8];
+      agen_pre(kc0, ri, h);
+#pragma unroll 1
+      for (int kc = kc0; kc + 1 < kc1; ++kc) {
+        uint32_t hn[8];
+        agen_pre(kc + 1, ri, hn);
+        agen_post(j, kc, h, std::false_type{});
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = hn[i];
+      }
+      agen_post(j, kc1 - 1, h, std::true_type{});
+      agen_flush();
+    };
 
     if (n_iter > 0) {
       tile_setup(fetch_tile(0), 0);
       named_bar_sync(1, EDGE_CT);
       const RowIn ri0 = row_inputs(0);
       mbar_wait(pq_full, 0u);
-#pragma unroll 1
-      for (int kc = 0; kc < E3_NKC; ++kc) agen_chunk(0, kc, ri0);
-      agen_flush();
+      agen_run(0, 0, E3_NKC, ri0);
       __syncwarp();
       if (lane == 0) mbar_arrive(pq_empty);
     }
@@ -581,9 +670,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
         rin = row_inputs(buf ^ 1);
         mbar_wait(pq_full, (uint32_t)((it + 1) & 1));
         tick(4);
-#pragma unroll 1
-        for (int kc = 0; kc < E3_EARLY; ++kc) agen_chunk(it + 1, kc, rin);
-        agen_flush();
+        agen_run(it + 1, 0, E3_EARLY, rin);
       }
       tick(5);
       pass1(std::integral_constant<int, 2>{});
@@ -615,9 +702,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
         }
         tick(9);
         if (has_next) {
-#pragma unroll 1
-          for (int kc = E3_EARLY; kc < E3_NKC; ++kc) agen_chunk(it + 1, kc, rin);
-          agen_flush();
+          agen_run(it + 1, E3_EARLY, E3_NKC, rin);
           __syncwarp();
           if (lane == 0) mbar_arrive(pq_empty);
         }
@@ -650,9 +735,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
         if (lane == 0) arrive_leader(e_full);
         tick(9);
         if (has_next) {
-#pragma unroll 1
-          for (int kc = E3_EARLY; kc < E3_NKC; ++kc) agen_chunk(it + 1, kc, rin);
-          agen_flush();
+          agen_run(it + 1, E3_EARLY, E3_NKC, rin);
           __syncwarp();
           if (lane == 0) mbar_arrive(pq_empty);
         }

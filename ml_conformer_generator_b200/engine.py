@@ -313,7 +313,7 @@ class Engine:
         self._check(self.lib.mlcg_edge_phase_profile(self.h, layer, out, self._stream()), "edge_phase_profile")
         names = ["rowinfo_pq_wait", "a_gen", "mma_tail", "pass1", "pass2", "a_ring_backpressure", "tiles",
                  "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout", "a_handoff"]
-        if self.precision in ("fp16", "bf16") and os.environ.get("MLCG_EDGE_V3", "0") != "0" and \
+        if self.precision in ("fp16", "bf16") and os.environ.get("MLCG_EDGE_V3", "1") != "0" and \
                 os.environ.get("MLCG_EDGE_PAIR", "1") != "0":
             # k_tc_edge3 (mlcg_tc3.cuh): per tile, thread 0 of the compute warps; the last two are the MMA issuer's waits
             # (leader CTAs only, i.e. half the per-tile value)
