@@ -26,6 +26,7 @@
 // D2 lands in the accumulator that the tile's last third used (free until the next tile's second third needs it).
 #pragma once
 #include <type_traits>
+#include <utility>
 #include "mlcg_tc.cuh"
 
 namespace mlcg {
@@ -57,7 +58,9 @@ struct Edge3Smem {
   static constexpr int WCD_OFF = WV_OFF + HP * 4;   // first-layer columns of the two distance features: wc[448] | wd[448] fp32, or
                                                    // the packed 16-bit table wcd_h[448]
   static constexpr int BAR_OFF = WCD_OFF + 2 * HP * 4;
-  static constexpr int PROF_OFF = BAR_OFF + 1024;  // barriers: 3 per W slot + 2 per K chunk + 10, then the TMEM slot   // 16 x int64 phase counters (diagnostics)
+  static constexpr int XT_OFF = BAR_OFF + 1024;    // barriers: 3 per W slot + 2 per K chunk + 10, then the TMEM slot.
+                                                   // XT: [2][12 x 3] coordinates of the tile's targets (equivariant layer)
+  static constexpr int PROF_OFF = XT_OFF + 512;   // 16 x int64 phase counters (diagnostics)
   static constexpr int TOTAL = PROF_OFF + 128;
   static constexpr int ALLOC = TOTAL + 1024;
   static_assert(STG_OFF % 1024 == 0 && SEL_OFF % 1024 == 0, "operand blocks must be 1024-byte aligned");
@@ -149,6 +152,25 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return done != 0;
 }
 
+// Order in which the 21 (third, K chunk) blocks of a tile are streamed and multiplied; returns third * 8 + chunk.
+//   sequential : third 0, third 1, third 2, chunks ascending.
+//   interleaved: the second third trails the first by two chunks WHILE the A operand is being generated --
+//                (0,0) (0,1) (0,2) (1,0) (0,3) (1,1) ... (0,6) (1,4) (1,5) (1,6), then third 2.  Both accumulators are then final
+//                right after the last A chunk, and the tensor core has worked through the stretch in which it otherwise only
+//                waits for A chunks.  Needs the second accumulator free before the tile's third A chunk is published: true
+//                for the equivariant variant (released after pass 1 of the previous tile's last third), not for GCL (it
+//                holds the segment sums until the readout at the end of the A generation).
+__host__ __device__ constexpr int e3_blk(bool interleave, int b) {
+  if (!interleave || b >= 14) return (b / 7) * 8 + (b % 7);
+  if (b < 2) return b;
+  if (b <= 10) return (b & 1) ? 8 + (b - 3) / 2 : b / 2 + 1;
+  return 8 + (b - 7);
+}
+template <class F, int... Bs>
+__device__ __forceinline__ void e3_for_blocks(F&& f, std::integer_sequence<int, Bs...>) {
+  (f(std::integral_constant<int, Bs>{}), ...);
+}
+
 // mbarrier slots of k_tc_edge3 (8 bytes each, from BAR_OFF)
 template <int NW>
 struct E3Bar {
@@ -180,33 +202,28 @@ __device__ __forceinline__ void edge3_issuer(int n_iter_in) {
   const uint64_t w_desc0 = umma_desc_sw128(base + S::W_OFF);
   uint32_t ws = 0, wph = 0;  // current W ring slot and its phase parity
   for (int it = 0; it < n_iter; ++it) {
-    auto third = [&](auto n3c) {
-      constexpr int n3 = decltype(n3c)::value;
-      const int G = 3 * it + n3, acc = G & 1, u = G >> 1;
-      if (G >= 2) mbar_wait_lean_w(bar0 + 8u * (B::D_FREE + acc), (uint32_t)((u - 1) & 1));
-      tc_fence_after();
-      const uint32_t dcol = tmem_base + E3_DCOL0 + acc * E3_NT;
+    e3_for_blocks(
+        [&](auto bc) {
+          constexpr int blk = e3_blk(!kSeg, decltype(bc)::value), n3 = blk >> 3, kc = blk & 7;
+          const int G = 3 * it + n3, acc = G & 1, u = G >> 1;
+          // first block of a third: its accumulator has been read out (pass 1 / segment-sum readout of its previous content)
+          if (kc == 0 && G >= 2) mbar_wait_lean_w(bar0 + 8u * (B::D_FREE + acc), (uint32_t)((u - 1) & 1));
+          // first third: the A chunk has just been generated; the later thirds reuse it
+          if (n3 == 0) mbar_wait_lean_w(bar0 + 8u * (B::A_FULL + kc), (uint32_t)(it & 1));
+          mbar_wait_lean_w(bar0 + 8u * (B::W_FULL + ws), wph);  // both halves of the block: own bulk copy + the peer's relay
+          tc_fence_after();
+          const uint32_t dcol = tmem_base + E3_DCOL0 + acc * E3_NT;
+          const uint64_t bdesc = w_desc0 + (uint64_t)(ws * (E3_WSLOT >> 4));
+          // the last chunk's fourth k-step (K 432..447) is all padding: A and W2 are zero there
 #pragma unroll
-      for (int kc = 0; kc < E3_NKC; ++kc) {
-        if (n3 == 0) {
-          mbar_wait_lean_w(bar0 + 8u * (B::A_FULL + kc), (uint32_t)(it & 1));
-        }
-        mbar_wait_lean_w(bar0 + 8u * (B::W_FULL + ws), wph);  // both halves of the block: own bulk copy + the peer's relay
-        tc_fence_after();
-        const uint64_t bdesc = w_desc0 + (uint64_t)(ws * (E3_WSLOT >> 4));
-        // the last chunk's fourth k-step (K 432..447) is all padding: A and W2 are zero there
-#pragma unroll
-        for (int ks = 0; ks < ((kc == E3_NKC - 1) ? 3 : 4); ++ks)
-          umma_ts_pair_e(dcol, tmem_base + kc * 32 + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
-        umma_commit_pair_e(bar0 + 8u * (B::W_EMPTY + ws), 3);
-        if (n3 == 2) umma_commit_pair_e(bar0 + 8u * (B::A_FREE + kc), 3);  // the next tile's A chunk kc may be written
-        if (++ws == NW) { ws = 0; wph ^= 1u; }
-      }
-      umma_commit_pair_e(bar0 + 8u * (B::D_FULL + acc), 3);
-    };
-    third(std::integral_constant<int, 0>{});
-    third(std::integral_constant<int, 1>{});
-    third(std::integral_constant<int, 2>{});
+          for (int ks = 0; ks < ((kc == E3_NKC - 1) ? 3 : 4); ++ks)
+            umma_ts_pair_e(dcol, tmem_base + kc * 32 + ks * 8, bdesc + 2 * ks, idesc, (kc | ks) != 0);
+          umma_commit_pair_e(bar0 + 8u * (B::W_EMPTY + ws), 3);
+          if (n3 == 2) umma_commit_pair_e(bar0 + 8u * (B::A_FREE + kc), 3);  // the next tile's A chunk kc may be written
+          if (kc == E3_NKC - 1) umma_commit_pair_e(bar0 + 8u * (B::D_FULL + acc), 3);
+          if (++ws == NW) { ws = 0; wph ^= 1u; }
+        },
+        std::make_integer_sequence<int, 3 * E3_NKC>{});
   }
 }
 
@@ -253,6 +270,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
   float2* ri_d_all = reinterpret_cast<float2*>(gbase + S::RID_OFF);
   int* ri_gj_all = reinterpret_cast<int*>(gbase + S::RIG_OFF);
   float* wv_s = reinterpret_cast<float*>(gbase + S::WV_OFF);
+  [[maybe_unused]] float* xt_all = reinterpret_cast<float*>(gbase + S::XT_OFF);
   const uint32_t bar0 = base + S::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
   auto w_empty = [&](int s) { return bar0 + 8u * (E3_NW + s); };
@@ -367,13 +385,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
     uint32_t ws = 0, wph = 1;  // slot and the parity of "empty" to wait for (first pass: slots start empty)
     const uint8_t* wsrc = p.w2 + (size_t)(72 * crank) * CHUNK_BYTES;
     for (int it = 0; it < n_iter; ++it) {
-#pragma unroll
-      for (int n3 = 0; n3 < 3; ++n3) {
-#pragma unroll
-        for (int kc = 0; kc < E3_NKC; ++kc) {
+      e3_for_blocks(
+          [&](auto bc) {
+          constexpr int blk = e3_blk(!kSeg, decltype(bc)::value), n3 = blk >> 3, kc = blk & 7;
           // the next tile's P/Q rows: requested once the second third is under way (the A generation of this tile is
           // complete by then, so pq_empty does not block the weight stream), needed one third later
-          if (n3 == 1 && kc == 5 && it + 1 < n_iter) load_pq(it + 1);
+          // (interleaved order with its deep ring: this warp runs up to 16 blocks ahead of the MMAs, so the request sits in the
+          // last third -- earlier it would wait for pq_empty with the second third's last blocks still unrequested)
+          if (n3 == (kSeg ? 1 : 2) && kc == (kSeg ? 5 : 2) && it + 1 < n_iter) load_pq(it + 1);
           if constexpr (kSeg) {
             // the previous tile's segment sum: its messages are staged and its selector is built once the compute warps are
             // through pass 1 of its last third, i.e. while they generate this tile's A chunks 2..; the weight blocks up to
@@ -388,8 +407,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
           bulk_g2s_expect_e(base + S::W_OFF + ws * E3_WSLOT, wsrc + (size_t)kc * (HP * CHUNK_BYTES) + (size_t)(E3_NT * n3) * CHUNK_BYTES,
                             E3_WSLOT, w_full(ws));
           if (++ws == E3_NW) { ws = 0; wph ^= 1u; }
-        }
-      }
+          },
+          std::make_integer_sequence<int, 3 * E3_NKC>{});
     }
     if constexpr (kSeg) {
       if (crank == 0 && n_iter > 0) {  // the last tile's segment sum
@@ -463,6 +482,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
           float* tr = trs_all + buf * TILE_M * 3 + rr * 3;
           tr[0] = dx * inv; tr[1] = dy * inv; tr[2] = dz * inv;
         }
+      } else if constexpr (kEquiv) {
+        // the targets' coordinates, for the update at the end of the tile: loaded a tile ahead so that the coordinate sums do
+        // not end in an exposed global-memory round trip
+        const int k = ct - TILE_M;
+        if (k < ti.ng * 3) xt_all[buf * 48 + k] = p.x_cur[(size_t)(node0 + i0) * 3 + k];
       }
     };
     auto pack_dist = [&](float d) {
@@ -527,6 +551,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
         for (int i = 0; i < 4; ++i) {
           uint32_t h2 = hadd2<kMode>(pa[i], qa[i]);
           if constexpr (kDistF32) {
+            // (an fp32 SiLU before the packing -- two issue cycles per pair fewer on paper, the packed 16-bit operations
+            // issue at half rate -- measured 1.5 % slower and no more accurate: rejected)
             const float h_lo = fmaf(ri.rd.y, wdv[2 * i], fmaf(ri.rd.x, wcv[2 * i], h2_lo<kMode>(h2)));
             const float h_hi = fmaf(ri.rd.y, wdv[2 * i + 1], fmaf(ri.rd.x, wcv[2 * i + 1], h2_hi<kMode>(h2)));
             h2 = pack_h2<kMode>(h_lo, h_hi);
@@ -698,7 +724,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
           if (carried_in(gg)) s = carry_rd[448 + c] + s;
           if (carried_out(gg)) carry_wr[448 + c] = s;
           else if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
-          else p.x_next[idx] = p.x_cur[idx] + s / 100.0f;
+          else p.x_next[idx] = xt_all[buf * 48 + gg * 3 + c] + s / 100.0f;
         }
         tick(9);
         if (has_next) {
