@@ -535,7 +535,7 @@ def main():
                      "d2h_bytes_per_step": d2h} if e2e_ms == e2e_ms else None),
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "k_tc_edge (GCL sub-layer, %s)" % args.precision,
+            "roofline": {"bound": "tensor", "kernel": "k_tc_edge3 (GCL sub-layer, %s)" % args.precision,
                          "achieved": achieved, "peak": pk["burst"], "unit": "TFLOP/s", "frac": achieved / pk["burst"],
                          "traffic": traffic, "peak_source": pk["source"] + " bf16 dense burst",
                          "launch_ms": edge_ms, "alg_flops_per_launch": edge_flops,

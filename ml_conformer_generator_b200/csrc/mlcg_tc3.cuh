@@ -154,17 +154,18 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 
 // Order in which the 21 (third, K chunk) blocks of a tile are streamed and multiplied; returns third * 8 + chunk.
 //   sequential : third 0, third 1, third 2, chunks ascending.
-//   interleaved: the second third trails the first by two chunks WHILE the A operand is being generated --
-//                (0,0) (0,1) (0,2) (1,0) (0,3) (1,1) ... (0,6) (1,4) (1,5) (1,6), then third 2.  Both accumulators are then final
+//   interleaved: the second third runs alongside the first WHILE the A operand is being generated --
+//                (0,0) (0,1) (1,0) (1,1) (0,2) (1,2) (0,3) (1,3) ... (0,6) (1,6), then third 2.  Both accumulators are then final
 //                right after the last A chunk, and the tensor core has worked through the stretch in which it otherwise only
-//                waits for A chunks.  Needs the second accumulator free before the tile's third A chunk is published: true
-//                for the equivariant variant (released after pass 1 of the previous tile's last third), not for GCL (it
-//                holds the segment sums until the readout at the end of the A generation).
+//                waits for A chunks.  Needs the second accumulator free by the time the tile's third A chunk is generated: true
+//                for the equivariant variant (released after pass 1 of the previous tile's last third, which sits between the
+//                second and the third chunk), not for GCL (it holds the segment sums until the readout at the end of the A
+//                generation).
 __host__ __device__ constexpr int e3_blk(bool interleave, int b) {
   if (!interleave || b >= 14) return (b / 7) * 8 + (b % 7);
   if (b < 2) return b;
-  if (b <= 10) return (b & 1) ? 8 + (b - 3) / 2 : b / 2 + 1;
-  return 8 + (b - 7);
+  if (b < 4) return 8 + (b - 2);
+  return (b & 1) ? 8 + b / 2 : b / 2;
 }
 template <class F, int... Bs>
 __device__ __forceinline__ void e3_for_blocks(F&& f, std::integer_sequence<int, Bs...>) {

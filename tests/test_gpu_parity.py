@@ -130,10 +130,13 @@ print("ERR", rel_l2(out["tf32"], out["fp32"]), rel_l2(out["bf16"], out["fp32"]))
 
 
 @pytest.mark.parametrize("env", [{"MLCG_EDGE_PAIR": "0"}, {"MLCG_EDGE_SPLIT": "0"}, {"MLCG_EDGE_GRID": "37"},
-                                 {"MLCG_EDGE_PAIR": "0", "MLCG_EDGE_SPLIT": "0", "MLCG_EDGE_GRID": "5"}])
+                                 {"MLCG_EDGE_PAIR": "0", "MLCG_EDGE_SPLIT": "0", "MLCG_EDGE_GRID": "5"},
+                                 {"MLCG_EDGE_V3": "0"}, {"MLCG_EDGE_V3": "0", "MLCG_EDGE_GRID": "36"},
+                                 {"MLCG_EDGE_V3": "1", "MLCG_EDGE_GRID": "6"}, {"MLCG_EDGE_V3": "1", "MLCG_EDGE_SPLIT": "0"}])
 def test_kernel_variants_selected_by_environment(env):
     """The documented runtime switches select other variants of the same CUDA path: single-CTA edge kernel,
-    whole-target tiles, smaller grids (different CTA tile ranges, hence different carried / side-buffer split targets).
+    whole-target tiles, smaller grids (different CTA tile ranges, hence different carried / side-buffer split targets), the
+    single-accumulator pair kernel k_tc_edge (MLCG_EDGE_V3=0) instead of the default k_tc_edge3.
     Each must match the exact fp32 CUDA path on a batch of every size 1..39 (read once per process => subprocess)."""
     import os
     import subprocess
