@@ -209,6 +209,13 @@ int mlcg_shape_tanimoto(mlcg_handle* h, const float* ref_pts, int n_ref, const f
 int mlcg_plan_edge_tiles(const int32_t* n_nodes_host, int B, int N, int num_sms, int32_t* tiles_out, int32_t* owner_out,
                          int max_tiles, int32_t* n_fix_out);
 
+/* Host-only (no device, no handle): the order in which k_tc_edge3 -- the fused edge kernel of the 16-bit modes -- streams
+ * and multiplies the 21 (third of the output channels, K chunk) weight blocks of a tile.  out receives 21 values
+ * third * 8 + chunk.  equivariant = 0: GCL sub-layers (third 0, 1, 2, chunks ascending); 1: EquivariantUpdate sub-layers (the
+ * second third interleaved with the first while the A operand is generated).  Producer and MMA issuer both follow this
+ * table.  Returns 21. */
+int mlcg_edge_block_order(int equivariant, int32_t* out);
+
 /* 1 if any mlcg_decode since the last call produced a non-finite coordinate, else 0; clears the flag; synchronises `stream`.
  * A trajectory can diverge (random-init weights in inpaint mode do, in every precision -- the reference's own fp32 path goes
  * NaN too); in MLCG_PREC_FP16 it also happens when pairwise distances exceed ~1.6e4 (pre-activations leave the fp16 range;

@@ -679,6 +679,12 @@ static int plan_edge_tiles(const int32_t* n_nodes, int B, int N, int num_sms, st
 
 /* Test / introspection hook (no device needed): the edge-tile plan for a batch as 8 ints per tile (EdgeTile) and the
  * CTA that owns each tile.  Returns the number of tiles (or < 0); fills at most max_tiles entries. */
+extern "C" int mlcg_edge_block_order(int equivariant, int32_t* out) {
+  if (!out) return MLCG_E_ARG;
+  for (int b = 0; b < 3 * E3_NKC; ++b) out[b] = e3_blk(equivariant != 0, b);
+  return 3 * E3_NKC;
+}
+
 extern "C" int mlcg_plan_edge_tiles(const int32_t* n_nodes, int B, int N, int num_sms, int32_t* tiles_out, int32_t* owner_out,
                                     int max_tiles, int32_t* n_fix_out) {
   if (!n_nodes || B <= 0 || N <= 0 || N > EDGE_MAXN || num_sms <= 0) return MLCG_E_ARG;

@@ -99,3 +99,32 @@ def test_plan_occupancy_and_errors():
     bad = np.array([40], np.int32)
     assert lib.mlcg_plan_edge_tiles(bad.ctypes.data, 1, 39, 148, None, None, 0, None) < 0
     assert lib.mlcg_plan_edge_tiles(bad.ctypes.data, 1, 64, 148, None, None, 0, None) < 0   # N > 39 is refused
+
+
+def test_edge3_block_order():
+    """k_tc_edge3: the static order of the 21 (third, K chunk) weight blocks of a tile that producer and MMA
+    issuer share.  Both variants visit every block once, keep each third's chunks ascending (the first MMA of a third
+    overwrites its accumulator), never multiply chunk k of the second third before chunk k of the first has been generated
+    (the first third is the one that waits for the A chunks), and run the last third after the other two (it releases the A
+    chunks for the next tile, and its accumulator is the first third's)."""
+    lib = _lib.load()
+    for equiv in (0, 1):
+        out = np.zeros(21, np.int32)
+        assert lib.mlcg_edge_block_order(equiv, out.ctypes.data) == 21
+        blocks = [(int(v) >> 3, int(v) & 7) for v in out]
+        assert sorted(blocks) == [(t, k) for t in range(3) for k in range(7)]
+        pos = {b: i for i, b in enumerate(blocks)}
+        for t in range(3):
+            assert [pos[(t, k)] for k in range(7)] == sorted(pos[(t, k)] for k in range(7))
+        for k in range(7):
+            assert pos[(0, k)] < pos[(1, k)] < pos[(2, k)]
+        assert min(pos[(2, k)] for k in range(7)) > max(pos[(t, k)] for t in (0, 1) for k in range(7))
+    seq = np.zeros(21, np.int32)
+    lib.mlcg_edge_block_order(0, seq.ctypes.data)
+    assert [(int(v) >> 3, int(v) & 7) for v in seq] == [(t, k) for t in range(3) for k in range(7)]
+    il = np.zeros(21, np.int32)
+    lib.mlcg_edge_block_order(1, il.ctypes.data)
+    # the equivariant order starts on the second third after two chunks (its accumulator is released between the second and
+    # the third A chunk of the tile) and then alternates
+    assert [(int(v) >> 3, int(v) & 7) for v in il[:6]] == [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (1, 2)]
+    assert lib.mlcg_edge_block_order(0, None) < 0
