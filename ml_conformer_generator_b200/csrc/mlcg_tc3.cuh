@@ -251,8 +251,8 @@ __device__ __forceinline__ void edge3_issue_seg(uint32_t base, int j) {
 // kProf: phase cycle counters (mlcg_edge_phase_profile): thread ct == 0 of every CTA accumulates [0] wait third 0, [1] pass 1
 // of third 0, [2] wait third 1, [3] pass 1 of third 1, [4] barrier + P/Q wait, [5] early A chunks of the next tile, [6] tiles,
 // [7] wait third 2, [8] pass 1 of third 2, [9] gate + selector + publish (equivariant: coordinate sums), [10] remaining A
-// chunks of the next tile, [11] wait for the segment-sum MMAs, [12] readout, [13] end-of-tile barrier; the MMA issuer of the
-// leader CTA adds [14] waiting for A chunks and [15] waiting for W2 blocks.
+// chunks of the next tile, [11] wait for the segment-sum MMAs, [12] readout, [13] end-of-tile barrier; [14], [15] unused (the
+// service warps carry no counters: their instruction streams are the thing to keep short).
 template <int kMode, bool kEquiv, bool kDistF32, bool kProf = false>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_constant__ EdgeArgs p) {
   static_assert(is16(kMode), "k_tc_edge3 serves the 16-bit tensor-core modes");
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
   const uint32_t bar0 = base + S::BAR_OFF;
   auto w_full = [&](int s) { return bar0 + 8u * s; };
   auto w_empty = [&](int s) { return bar0 + 8u * (E3_NW + s); };
-  auto w_peer = [&](int s) { return bar0 + 8u * (2 * E3_NW + s); };        // leader: the peer's half of slot s has landed
+  // (slots 2 NW .. 3 NW - 1 are unused: the peer's relay arrives on the leader's w_full, whose count is 2)
   auto a_full = [&](int kc) { return bar0 + 8u * (3 * E3_NW + kc); };      // leader: A chunk kc of the current tile is in TMEM
   auto a_free = [&](int kc) { return bar0 + 8u * (3 * E3_NW + E3_NKC + kc); };  // the last third has consumed A chunk kc
   const uint32_t pq_full = bar0 + 8u * (3 * E3_NW + 2 * E3_NKC);
@@ -317,7 +317,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
     for (int s = 0; s < E3_NW; ++s) {
       mbar_init(w_full(s), crank == 0 ? 2 : 1);  // leader: own producer (expect_tx) + the peer's relay
       mbar_init(w_empty(s), 1);
-      mbar_init(w_peer(s), 1);
     }
     for (int kc = 0; kc < E3_NKC; ++kc) {
       mbar_init(a_full(kc), NARR);

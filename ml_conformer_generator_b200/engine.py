@@ -315,11 +315,11 @@ class Engine:
                  "p2_wait_segmma", "p2_load_gate_pack", "p2_stage_arrive", "p2_readout", "a_handoff"]
         if self.precision in ("fp16", "bf16") and os.environ.get("MLCG_EDGE_V3", "1") != "0" and \
                 os.environ.get("MLCG_EDGE_PAIR", "1") != "0":
-            # k_tc_edge3 (mlcg_tc3.cuh): per tile, thread 0 of the compute warps; the last two are the MMA issuer's waits
-            # (leader CTAs only, i.e. half the per-tile value)
+            # k_tc_edge3 (mlcg_tc3.cuh): per tile, thread 0 of the compute warps (the highest-priority warp of its
+            # sub-partition: it finishes the MUFU-bound phases first and waits at the barriers for the others)
             names = ["wait_third0", "pass1_third0", "wait_third1", "pass1_third1", "barrier_pq_wait", "agen_early", "tiles",
                      "wait_third2", "pass1_third2", "gate_selector", "agen_rest", "wait_segsum", "readout", "end_barrier",
-                     "issuer_wait_a", "issuer_wait_w"]
+                     "unused14", "unused15"]
         return {n: float(out[i]) for i, n in enumerate(names)}
 
     def gemm_phase_profile(self, which: int) -> dict:
