@@ -250,8 +250,8 @@ __device__ __forceinline__ void edge3_issue_seg(uint32_t base, int j) {
 
 // kProf: phase cycle counters (mlcg_edge_phase_profile): thread ct == 0 of every CTA accumulates [0] wait third 0, [1] pass 1
 // of third 0, [2] wait third 1, [3] pass 1 of third 1, [4] barrier + P/Q wait, [5] early A chunks of the next tile, [6] tiles,
-// [7] wait third 2, [8] pass 1 of third 2, [9] gate + selector + publish (equivariant: coordinate sums), [10] remaining A
-// chunks of the next tile, [11] wait for the segment-sum MMAs, [12] readout, [13] end-of-tile barrier; [14], [15] unused (the
+// [7] wait third 2, [8] pass 1 of third 2, [9] gate + selector + publish (equivariant: remaining A chunks of the next tile), [10]
+// remaining A chunks of the next tile (equivariant: coordinate sums), [11] wait for the segment-sum MMAs, [12] readout, [13] end-of-tile barrier; [14], [15] unused (the
 // service warps carry no counters: their instruction streams are the thing to keep short).
 template <int kMode, bool kEquiv, bool kDistF32, bool kProf = false>
 __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_constant__ EdgeArgs p) {
@@ -703,6 +703,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
       dots[qq * TILE_M + r] = (dotp[0] + dotp[1]) + (dotp[2] + dotp[3]);
       named_bar_sync(1, EDGE_CT);
       if constexpr (kEquiv) {
+        // The next tile's remaining A chunks first, the coordinate sums after them: the sums are a short dependent chain in 9 of
+        // the 16 warps; placed before the A generation, the other 7 warps ran ahead into it and the chain crawled behind them
+        // (1.7 k cycles per tile), delaying A chunks that need all 16 warps.  dots / unit vectors / carry buffers are not
+        // touched in between (next written after the end-of-tile barrier).  (One warp per target instead of eight threads per
+        // (target, coordinate) measured 1 % slower.)
+        if (has_next) {
+          agen_run(it + 1, E3_EARLY, E3_NKC, rin);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pq_empty);
+        }
+        tick(9);
         // x_i += sum_j unit_ij * phi_ij / 100   (reference egnn.py:124-134).  Eight threads per (target, coordinate): each
         // sums every eighth row of the target's range (rows inside [glo, ghi) are valid by construction), then three
         // shuffle steps -- a fixed order, so the result is deterministic.
@@ -725,12 +736,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 1) k_tc_edge3(const __grid_const
           if (carried_out(gg)) carry_wr[448 + c] = s;
           else if (fx >= 0) atomicAdd(p.fix_dx + (size_t)fx * 4 + c, s);
           else p.x_next[idx] = xt_all[buf * 48 + gg * 3 + c] + s / 100.0f;
-        }
-        tick(9);
-        if (has_next) {
-          agen_run(it + 1, E3_EARLY, E3_NKC, rin);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pq_empty);
         }
         tick(10);
       } else {
