@@ -316,7 +316,9 @@ class Engine:
         if self.precision in ("fp16", "bf16") and os.environ.get("MLCG_EDGE_V3", "1") != "0" and \
                 os.environ.get("MLCG_EDGE_PAIR", "1") != "0":
             # k_tc_edge3 (mlcg_tc3.cuh): per tile, thread 0 of the compute warps (the highest-priority warp of its
-            # sub-partition: it finishes the MUFU-bound phases first and waits at the barriers for the others)
+            # sub-partition: it finishes the MUFU-bound phases first and waits at the barriers for the others).
+            # Equivariant sub-layers: "gate_selector" holds the remaining A chunks of the next tile and "agen_rest" the
+            # coordinate sums (they run in that order there); "wait_segsum" / "readout" are GCL only.
             names = ["wait_third0", "pass1_third0", "wait_third1", "pass1_third1", "barrier_pq_wait", "agen_early", "tiles",
                      "wait_third2", "pass1_third2", "gate_selector", "agen_rest", "wait_segsum", "readout", "end_barrier",
                      "unused14", "unused15"]
