@@ -24,6 +24,17 @@
 // The segment sum (GCL) stays on the tensor core: the messages of all three thirds are staged in shared memory in natural
 // channel order ([channels x rows], MN-major A operand, 7 x 16 KB), the gate enters through the selector, and the result
 // D2 lands in the accumulator that the tile's last third used (free until the next tile's second third needs it).
+//
+// Warp roles (18 warps per CTA, CTA pairs):
+//   warp 0        bulk-copy producer (P/Q rows, 21 weight blocks per tile); in the leader CTA it also issues the 32
+//                 segment-sum MMAs of a GCL tile -- one thread cannot issue them AND the thirds at the tensor core's rate
+//   warp 1        leader CTA: tcgen05.mma issuer of the thirds (cta_group::2, M = 256); peer CTA: relays "my half of the
+//                 weight block has landed" onto the leader's barrier
+//   warps 2..17   compute: A generation, pass 1 per third, gate / selector / D2 readout or coordinate sums
+// All three service loops run with the whole warp converged and issue their tcgen05 / bulk-copy instructions from one elected
+// lane (elect.sync inside the asm); the equivariant variant multiplies the second third alongside the first while the A
+// operand is generated (e3_blk) and sums the coordinate messages after the next tile's A generation.
+// DESIGN.md 4.1b has the measurements behind each of these choices.
 #pragma once
 #include <type_traits>
 #include <utility>
